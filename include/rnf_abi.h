@@ -1,0 +1,153 @@
+/*
+ * rnf_abi.h -- C ABI of librnf_b200.so: the B200 (sm_100a) hot path of RotationNormFlow.
+ *
+ * The reference (PKU-EPIC/RotationNormFlow) is 100 % Python and has no FFI; its boundary for this
+ * path is the nn.Module protocol of flow/flow.py.  The entry points below are what a ctypes binding
+ * for that path binds (INTEGRATION.md shows the stub); each cites the reference interface it replaces.
+ * All file:line citations are relative to the reference repository root.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer named *_dev is DEVICE memory owned by the caller
+ *     (PyTorch allocates it); nothing here allocates device memory except rnf_flow_create's small
+ *     copy of the layer table.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default).
+ *   - return 0 on success, negative RNF_E* on argument errors, positive = cudaError_t.
+ *     rnf_last_error() returns a thread-local message for the last non-zero return.
+ *   - rotations are float32 [N,3,3] row-major (the layout of the reference's `rotation` tensors).
+ *   - re-entrant per (handle, stream); no global mutable state (nn.DataParallel-style concurrent
+ *     callers on different devices each own a handle; agent.py:22,53-54).
+ */
+#ifndef RNF_ABI_H_
+#define RNF_ABI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RNF_ABI_VERSION 3
+
+/* error codes */
+#define RNF_OK 0
+#define RNF_EINVAL (-1)   /* bad argument (null pointer, negative size, bad enum)   */
+#define RNF_ESHAPE (-2)   /* model dimensions unsupported by the compiled kernels   */
+#define RNF_ENODEV (-3)   /* no CUDA device / device is not sm_100                  */
+#define RNF_ESTATE (-4)   /* handle is not usable for this call (e.g. no features)  */
+
+/* layer kinds (flow/flow.py:36-51 builds a list of exactly these two families) */
+#define RNF_LAYER_MOBIUS 0 /* flow/mobiusflow.py:27-183  MobiusFlow                                   */
+#define RNF_LAYER_AFFINE 1 /* flow/squeezetrans.py:33-38 calculate_16, and flow/rottrans.py:8-66 (has_ldj=0) */
+
+/* kernel selection for the conditioner MLP (flow/condition.py:24-30) */
+#define RNF_MLP_FP32 0    /* FP32 CUDA-core FMA: the exact-precision path                             */
+#define RNF_MLP_TC 1      /* tcgen05 tensor cores, error-compensated split operands, FP32 accumulate  */
+
+/*
+ * One entry per layer, in module order (index i == `layers.{i}` of the reference state dict).
+ *   perm      : row r of the cyclic table flow/flow.py:13-15 reduced mod 3; the layer acts on columns
+ *               (r, r+1, r+2) mod 3 of R.  Ignored by affine layers.
+ *   cond_slot : >= 0 -> this layer reads per-image data produced by rnf_flow_condition():
+ *                 Mobius: 64 floats  W_f.feature  (first conditioner layer hoisted per image)
+ *                 affine: the 4x4 matrix of Condition16Trans / ConditionRot for that image
+ *               -1 -> unconditional.
+ *   has_ldj   : affine only. 1 = log|det W| - 4 log|Wq| (squeezetrans.py:38); 0 = rotation layer (rottrans.py:21).
+ *   w_off     : float offset of this layer's block inside the packed weight buffer (layout: DESIGN.md).
+ */
+typedef struct rnf_layer_desc {
+  int32_t kind;
+  int32_t perm;
+  int32_t cond_slot;
+  int32_t has_ldj;
+  int64_t w_off;
+  int64_t w_off_tc;   /* offset of the tensor-core (split fp16) image of the conditioner, -1 if absent */
+} rnf_layer_desc;
+
+typedef struct rnf_model_desc {
+  int32_t abi_version;    /* RNF_ABI_VERSION                                                        */
+  int32_t n_layers;
+  int32_t K;              /* Mobius mixture components (config.segments); kernels are built for 64   */
+  int32_t H;              /* conditioner hidden width (flow/condition.py:9 Nh); kernels built for 64 */
+  int32_t F;              /* feature width seen by the flow (0 = unconditional)                      */
+  int32_t n_mobius_slots; /* conditional Mobius layers                                               */
+  int32_t n_affine_slots; /* conditional affine / rot layers                                         */
+  int32_t affine_is_rot;  /* 1: conditional affine slots are ConditionRot (SVD polar factor)          */
+  int64_t wf_off;         /* [n_mobius_slots + n_affine_slots][H][F] first-layer feature weights     */
+  int64_t caff_off;       /* [n_affine_slots] blocks of the conditional-affine MLP tails             */
+  int64_t n_floats;       /* total floats in the packed buffer                                       */
+} rnf_model_desc;
+
+typedef struct rnf_flow rnf_flow;
+
+int rnf_abi_version(void);
+const char* rnf_last_error(void);
+
+/* Number of SMs / device check: 0 if the current device is sm_100, else RNF_ENODEV. */
+int rnf_device_check(int* sm_count_out);
+
+/*
+ * Replaces Flow.__init__ / get_flow (flow/flow.py:9-51) for the device side: registers the layer table
+ * and the packed weights (device pointer, caller-owned, must outlive the handle).
+ */
+int rnf_flow_create(const rnf_model_desc* model, const rnf_layer_desc* layers,
+                    const float* weights_dev, rnf_flow** out);
+void rnf_flow_destroy(rnf_flow* flow);
+
+/* Floats per image in the buffer written by rnf_flow_condition (0 for an unconditional flow). */
+int64_t rnf_flow_cond_floats(const rnf_flow* flow);
+
+/*
+ * Per-image part of the conditioners: replaces, for every conditional layer at once, the feature columns of
+ * fc_first in ConditionalTransform.forward (flow/condition.py:25, input built at flow/mobiusflow.py:54) and the
+ * whole Condition16Trans / ConditionRot matrix network (flow/squeezetrans.py:47-54, flow/rottrans.py:43-46),
+ * including the inverse-direction matrices (torch.linalg.inv, squeezetrans.py:54 / transpose, rottrans.py:58).
+ *   feat_dev [B,F] float32 row-major  ->  cond_dev [B, rnf_flow_cond_floats()]
+ */
+int rnf_flow_condition(rnf_flow* flow, const float* feat_dev, int64_t B, float* cond_dev, void* stream);
+
+/*
+ * Flow.forward (flow/flow.py:53-72) and Flow.inverse (flow/flow.py:74-92).
+ *   R_in_dev  [N,3,3]   rotations (not modified)
+ *   cond_dev  [B,cond_floats] from rnf_flow_condition, NULL for an unconditional flow
+ *   row -> image mapping (the reference takes a row-aligned `feature [N,F]`, built by .repeat at
+ *   agent.py:240-244 / eval.py:450):  feat_index_dev[row] if non-NULL, else row / rows_per_image.
+ *   R_out_dev [N,3,3], ldj_out_dev [N]
+ *   scratch_dev : inverse only, rnf_flow_inverse_scratch_floats() floats (bisection parameters).
+ */
+int rnf_flow_forward(rnf_flow* flow, const float* R_in_dev, int64_t N, const float* cond_dev, int64_t B,
+                     const int32_t* feat_index_dev, int64_t rows_per_image, float* R_out_dev,
+                     float* ldj_out_dev, int mlp_mode, void* stream);
+int64_t rnf_flow_inverse_scratch_floats(const rnf_flow* flow, int64_t N);
+int rnf_flow_inverse(rnf_flow* flow, const float* R_in_dev, int64_t N, const float* cond_dev, int64_t B,
+                     const int32_t* feat_index_dev, int64_t rows_per_image, float* R_out_dev,
+                     float* ldj_out_dev, float* scratch_dev, int mlp_mode, void* stream);
+
+/*
+ * Grid evaluation: the inner loops of eval.py:444-462 (gradient()) and agent.py:246-266 fused:
+ * for every image b < B and every grid rotation g in [0,G):
+ *     R = grid[g] @ offset            (eval.py:439-440; offset NULL = identity)
+ *     (R', ldj) = Flow.forward(R, feature_b)
+ *     logp[b,g] = ldj + [ sum(A_b * R') - sumS_b - logc_b ]     (utils/fisher.py:217-232, if fisher_A_dev != NULL)
+ * and per image the running (max, first arg-max index, sum exp(logp - max)) over this call's grid slice.
+ *   grid_dev      [G,3,3] this rank's slice of the grid;  g_index0 = global index of its first rotation
+ *   fisher_A_dev  [B,9], fisher_c_dev [B] = sumS_b + logc_b   (both NULL for no base term)
+ *   logp_out_dev  [B,G] or NULL
+ *   part_dev      workspace, rnf_grid_partial_floats(G, B) floats
+ *   max_out_dev [B] float, argmax_out_dev [B] int64 (global index), sumexp_out_dev [B] float (relative to max_out)
+ */
+int64_t rnf_grid_partial_floats(int64_t G, int64_t B);
+int rnf_grid_logprob(rnf_flow* flow, const float* grid_dev, int64_t G, int64_t g_index0, const float* offset_dev,
+                     const float* cond_dev, int64_t B, const float* fisher_A_dev, const float* fisher_c_dev,
+                     float* logp_out_dev, float* part_dev, float* max_out_dev, int64_t* argmax_out_dev,
+                     float* sumexp_out_dev, int mlp_mode, void* stream);
+
+/*
+ * generate_healpix_grid (utils/sd.py:48-82): rotations [begin,end) of the level-`level` grid
+ * (72*8^level rotations, index = tilt*npix + pixel, RING pixel order), float64 math -> float32.
+ */
+int rnf_healpix_grid(int level, int64_t begin, int64_t end, float* R_out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNF_ABI_H_ */

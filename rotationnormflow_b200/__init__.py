@@ -1,0 +1,10 @@
+"""rotationnormflow_b200 -- B200-native (sm_100a) hot path of RotationNormFlow: evaluating and inverting the
+composed discrete normalizing flow on SO(3).  Drop-in for the reference's ``flow/flow.py`` API; the compute lives in
+``librnf_b200.so`` (hand-written CUDA, C ABI in ``include/rnf_abi.h``).  No CPU fallback."""
+from .config import load_config
+from .flow import (ConditionalTransform, Condition16Trans, ConditionRot, Flow, MobiusFlow, Uncondition16Trans,
+                   Uncondition16TransLU, UnconditionLU, UnconditionRot, get_affine, get_flow, get_mobius)
+
+__all__ = ["load_config", "get_flow", "Flow", "MobiusFlow", "ConditionalTransform", "Uncondition16Trans",
+           "Uncondition16TransLU", "UnconditionLU", "Condition16Trans", "UnconditionRot", "ConditionRot",
+           "get_affine", "get_mobius"]

@@ -1,0 +1,247 @@
+// rnf_abi.cu -- the extern "C" boundary declared in include/rnf_abi.h.  No torch types, no exceptions.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "rnf_common.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return (int)e;
+}
+
+bool valid_mode(int m) { return m == RNF_MLP_FP32 || m == RNF_MLP_TC; }
+
+}  // namespace
+
+namespace rnf {
+cudaError_t launch_flow_tc(const FlowArgs& a, bool inverse, int sm_count, cudaStream_t st);
+bool flow_tc_supported(const rnf_flow* f);
+}  // namespace rnf
+
+extern "C" {
+
+int rnf_abi_version(void) { return RNF_ABI_VERSION; }
+
+const char* rnf_last_error(void) { return g_err; }
+
+int rnf_device_check(int* sm_count_out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(RNF_ENODEV, "cudaGetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return fail(RNF_ENODEV, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10) return fail(RNF_ENODEV, "device %d is sm_%d%d; this library contains sm_100a code only", dev, prop.major, prop.minor);
+  if (sm_count_out) *sm_count_out = prop.multiProcessorCount;
+  return RNF_OK;
+}
+
+int rnf_flow_create(const rnf_model_desc* model, const rnf_layer_desc* layers, const float* weights_dev, rnf_flow** out) {
+  if (!model || !out || (model->n_layers > 0 && !layers)) return fail(RNF_EINVAL, "rnf_flow_create: null argument");
+  if (model->abi_version != RNF_ABI_VERSION)
+    return fail(RNF_EINVAL, "rnf_flow_create: ABI version %d, library is %d", model->abi_version, RNF_ABI_VERSION);
+  if (model->n_layers < 0 || model->F < 0) return fail(RNF_EINVAL, "rnf_flow_create: negative size");
+  if (model->K != rnf::kK || model->H != rnf::kH)
+    return fail(RNF_ESHAPE, "rnf_flow_create: kernels are built for segments=64, hidden=64 (got K=%d H=%d)", model->K, model->H);
+  if (model->n_floats > 0 && !weights_dev) return fail(RNF_EINVAL, "rnf_flow_create: null weights");
+  int n_mob = 0, n_aff = 0;
+  for (int i = 0; i < model->n_layers; ++i) {
+    const rnf_layer_desc& L = layers[i];
+    if (L.kind != RNF_LAYER_MOBIUS && L.kind != RNF_LAYER_AFFINE) return fail(RNF_EINVAL, "layer %d: bad kind %d", i, L.kind);
+    if (L.kind == RNF_LAYER_MOBIUS && (L.perm < 0 || L.perm > 2)) return fail(RNF_EINVAL, "layer %d: bad perm %d", i, L.perm);
+    if (L.w_off < 0 || (L.w_off & 3) || L.w_off > model->n_floats) return fail(RNF_EINVAL, "layer %d: bad weight offset", i);
+    if (L.cond_slot >= 0) {
+      if (model->F <= 0) return fail(RNF_EINVAL, "layer %d is conditional but F == 0", i);
+      if (L.kind == RNF_LAYER_MOBIUS) { if (L.cond_slot != n_mob++) return fail(RNF_EINVAL, "layer %d: Mobius slots must be consecutive", i); }
+      else { if (L.cond_slot != n_aff++) return fail(RNF_EINVAL, "layer %d: affine slots must be consecutive", i); }
+    }
+  }
+  if (n_mob != model->n_mobius_slots || n_aff != model->n_affine_slots)
+    return fail(RNF_EINVAL, "slot counts (%d,%d) do not match the layer table (%d,%d)", model->n_mobius_slots,
+                model->n_affine_slots, n_mob, n_aff);
+  int sm = 0;
+  int rc = rnf_device_check(&sm);
+  if (rc != RNF_OK) return rc;
+  rnf_flow* f = (rnf_flow*)calloc(1, sizeof(rnf_flow));
+  if (!f) return fail(RNF_EINVAL, "out of host memory");
+  f->model = *model;
+  f->weights_dev = weights_dev;
+  f->sm_count = sm;
+  cudaGetDevice(&f->device);
+  f->cond_floats = (int64_t)n_mob * rnf::kH + (int64_t)n_aff * (rnf::kAffFloats + rnf::kH);
+  const size_t bytes = sizeof(rnf_layer_desc) * (size_t)(model->n_layers > 0 ? model->n_layers : 1);
+  f->layers_host = (rnf_layer_desc*)malloc(bytes);
+  if (model->n_layers > 0) memcpy(f->layers_host, layers, sizeof(rnf_layer_desc) * model->n_layers);
+  static_assert(sizeof(rnf::LayerDev) == sizeof(rnf_layer_desc), "layer table layouts must agree");
+  cudaError_t e = cudaMalloc((void**)&f->layers_dev, bytes);
+  if (e == cudaSuccess && model->n_layers > 0)
+    e = cudaMemcpy(f->layers_dev, layers, sizeof(rnf_layer_desc) * model->n_layers, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    free(f->layers_host);
+    free(f);
+    return cuda_fail(e, "rnf_flow_create");
+  }
+  *out = f;
+  return RNF_OK;
+}
+
+void rnf_flow_destroy(rnf_flow* f) {
+  if (!f) return;
+  cudaFree(f->layers_dev);
+  free(f->layers_host);
+  free(f);
+}
+
+int64_t rnf_flow_cond_floats(const rnf_flow* f) { return f ? f->cond_floats : 0; }
+
+int rnf_flow_condition(rnf_flow* f, const float* feat_dev, int64_t B, float* cond_dev, void* stream) {
+  if (!f) return fail(RNF_EINVAL, "rnf_flow_condition: null handle");
+  if (f->cond_floats == 0) return fail(RNF_ESTATE, "rnf_flow_condition: the flow is unconditional");
+  if (B < 0 || (B > 0 && (!feat_dev || !cond_dev))) return fail(RNF_EINVAL, "rnf_flow_condition: bad arguments");
+  cudaError_t e = rnf::launch_condition(f, feat_dev, B, cond_dev, (cudaStream_t)stream);
+  return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_flow_condition");
+}
+
+static int run_rows(rnf_flow* f, bool inverse, const float* R_in, int64_t N, const float* cond, int64_t B,
+                    const int32_t* feat_index, int64_t rows_per_image, float* R_out, float* ldj_out, float* scratch,
+                    int mlp_mode, void* stream) {
+  const char* who = inverse ? "rnf_flow_inverse" : "rnf_flow_forward";
+  if (!f) return fail(RNF_EINVAL, "%s: null handle", who);
+  if (N < 0) return fail(RNF_EINVAL, "%s: negative N", who);
+  if (!valid_mode(mlp_mode)) return fail(RNF_EINVAL, "%s: bad mlp_mode %d", who, mlp_mode);
+  if (N == 0) return RNF_OK;
+  if (!R_in || !R_out || !ldj_out) return fail(RNF_EINVAL, "%s: null buffer", who);
+  if (f->cond_floats > 0) {
+    if (!cond || B <= 0) return fail(RNF_ESTATE, "%s: conditional flow needs the output of rnf_flow_condition", who);
+    if (!feat_index && rows_per_image <= 0) return fail(RNF_EINVAL, "%s: need feat_index or rows_per_image > 0", who);
+    if (!feat_index && (N + rows_per_image - 1) / rows_per_image > B)
+      return fail(RNF_EINVAL, "%s: N=%lld rows at %lld rows/image exceed B=%lld images", who, (long long)N,
+                  (long long)rows_per_image, (long long)B);
+  } else {
+    cond = nullptr;
+  }
+  if (inverse && !scratch) return fail(RNF_EINVAL, "%s: null scratch", who);
+  rnf::FlowArgs a;
+  memset(&a, 0, sizeof(a));
+  a.weights = f->weights_dev;
+  a.layers = f->layers_dev;
+  a.n_layers = f->model.n_layers;
+  a.n_mobius_slots = f->model.n_mobius_slots;
+  a.R_in = R_in;
+  a.N = N;
+  a.cond = cond;
+  a.cond_stride = f->cond_floats;
+  a.feat_index = feat_index;
+  a.rows_per_image = rows_per_image > 0 ? rows_per_image : 1;
+  a.R_out = R_out;
+  a.ldj_out = ldj_out;
+  a.scratch = scratch;
+  cudaError_t e;
+  if (mlp_mode == RNF_MLP_TC) {
+    if (!rnf::flow_tc_supported(f)) return fail(RNF_ESTATE, "%s: model was packed without the tensor-core weight image", who);
+    a.n_tiles = (N + 127) / 128;
+    e = rnf::launch_flow_tc(a, inverse, f->sm_count, (cudaStream_t)stream);
+  } else {
+    a.n_tiles = (N + rnf::kV1Threads - 1) / rnf::kV1Threads;
+    e = rnf::launch_flow_v1(a, inverse, f->sm_count, (cudaStream_t)stream);
+  }
+  return e == cudaSuccess ? RNF_OK : cuda_fail(e, who);
+}
+
+int rnf_flow_forward(rnf_flow* f, const float* R_in, int64_t N, const float* cond, int64_t B, const int32_t* feat_index,
+                     int64_t rows_per_image, float* R_out, float* ldj_out, int mlp_mode, void* stream) {
+  return run_rows(f, false, R_in, N, cond, B, feat_index, rows_per_image, R_out, ldj_out, nullptr, mlp_mode, stream);
+}
+
+int64_t rnf_flow_inverse_scratch_floats(const rnf_flow* f, int64_t N) {
+  if (!f || N <= 0) return 0;
+  const int64_t tiles = (N + rnf::kV1Threads - 1) / rnf::kV1Threads;
+  const int64_t ctas = tiles < f->sm_count ? tiles : f->sm_count;
+  return ctas * 4 * rnf::kK * rnf::kV1Threads;
+}
+
+int rnf_flow_inverse(rnf_flow* f, const float* R_in, int64_t N, const float* cond, int64_t B, const int32_t* feat_index,
+                     int64_t rows_per_image, float* R_out, float* ldj_out, float* scratch, int mlp_mode, void* stream) {
+  return run_rows(f, true, R_in, N, cond, B, feat_index, rows_per_image, R_out, ldj_out, scratch, mlp_mode, stream);
+}
+
+int64_t rnf_grid_partial_floats(int64_t G, int64_t B) {
+  if (G <= 0 || B <= 0) return 0;
+  const int64_t tpi = (G + 127) / 128;  // sized for the smaller (tensor-core) tile so either kernel fits
+  return tpi * B * 4;
+}
+
+int rnf_grid_logprob(rnf_flow* f, const float* grid_dev, int64_t G, int64_t g_index0, const float* offset_dev,
+                     const float* cond_dev, int64_t B, const float* fisher_A_dev, const float* fisher_c_dev,
+                     float* logp_out_dev, float* part_dev, float* max_out_dev, int64_t* argmax_out_dev,
+                     float* sumexp_out_dev, int mlp_mode, void* stream) {
+  if (!f) return fail(RNF_EINVAL, "rnf_grid_logprob: null handle");
+  if (G < 0 || B < 0) return fail(RNF_EINVAL, "rnf_grid_logprob: negative size");
+  if (!valid_mode(mlp_mode)) return fail(RNF_EINVAL, "rnf_grid_logprob: bad mlp_mode %d", mlp_mode);
+  if (G == 0 || B == 0) return RNF_OK;
+  if (!grid_dev || !part_dev || !max_out_dev || !argmax_out_dev || !sumexp_out_dev)
+    return fail(RNF_EINVAL, "rnf_grid_logprob: null buffer");
+  if ((fisher_A_dev == nullptr) != (fisher_c_dev == nullptr))
+    return fail(RNF_EINVAL, "rnf_grid_logprob: fisher_A and fisher_c must be given together");
+  if (f->cond_floats > 0 && !cond_dev) return fail(RNF_ESTATE, "rnf_grid_logprob: conditional flow needs rnf_flow_condition output");
+  rnf::FlowArgs a;
+  memset(&a, 0, sizeof(a));
+  a.weights = f->weights_dev;
+  a.layers = f->layers_dev;
+  a.n_layers = f->model.n_layers;
+  a.n_mobius_slots = f->model.n_mobius_slots;
+  a.R_in = grid_dev;
+  a.N = G * B;
+  a.cond = f->cond_floats > 0 ? cond_dev : nullptr;
+  a.cond_stride = f->cond_floats;
+  a.rows_per_image = 1;
+  a.G = G;
+  a.g_index0 = g_index0;
+  a.offset = offset_dev;
+  a.fisher_A = fisher_A_dev;
+  a.fisher_c = fisher_c_dev;
+  a.logp_out = logp_out_dev;
+  a.part = part_dev;
+  cudaError_t e;
+  if (mlp_mode == RNF_MLP_TC) {
+    if (!rnf::flow_tc_supported(f)) return fail(RNF_ESTATE, "rnf_grid_logprob: model was packed without the tensor-core weight image");
+    a.tiles_per_image = (G + 127) / 128;
+    a.n_tiles = a.tiles_per_image * B;
+    e = rnf::launch_flow_tc(a, false, f->sm_count, (cudaStream_t)stream);
+  } else {
+    a.tiles_per_image = (G + rnf::kV1Threads - 1) / rnf::kV1Threads;
+    a.n_tiles = a.tiles_per_image * B;
+    e = rnf::launch_flow_v1(a, false, f->sm_count, (cudaStream_t)stream);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "rnf_grid_logprob");
+  e = rnf::launch_grid_combine(part_dev, a.tiles_per_image, B, g_index0, max_out_dev, argmax_out_dev, sumexp_out_dev,
+                               (cudaStream_t)stream);
+  return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_grid_logprob (combine)");
+}
+
+int rnf_healpix_grid(int level, int64_t begin, int64_t end, float* R_out_dev, void* stream) {
+  if (level < 0 || level > 8) return fail(RNF_EINVAL, "rnf_healpix_grid: level %d outside 0..8 (utils/sd.py:32)", level);
+  int64_t total = 72;
+  for (int i = 0; i < level; ++i) total *= 8;
+  if (begin < 0 || end < begin || end > total) return fail(RNF_EINVAL, "rnf_healpix_grid: bad range");
+  if (end == begin) return RNF_OK;
+  if (!R_out_dev) return fail(RNF_EINVAL, "rnf_healpix_grid: null output");
+  cudaError_t e = rnf::launch_healpix(level, begin, end, R_out_dev, (cudaStream_t)stream);
+  return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_healpix_grid");
+}
+
+}  // extern "C"

@@ -1,0 +1,292 @@
+"""Host side of the fused flow kernels: weight packing, handle management and launches.
+
+PyTorch is used here only as plumbing (device memory, the current CUDA stream, ``torch.svd`` / LU algebra on
+4x4 parameter matrices exactly where the reference calls them).  All per-rotation arithmetic runs inside
+``librnf_b200.so``; there is no CPU or eager-PyTorch path -- CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+K_SEGMENTS = 64   # kernels are specialised for the value every settings/*.yml uses
+HIDDEN = 64       # flow/condition.py:9 (Nh)
+
+# float sizes of the packed blocks; must mirror csrc/rnf_common.cuh
+MOB_FLOATS = 64 * 4 + 3 * (64 * 64 + 64) + 64 * 256 + 256
+AFF_FLOATS = 40
+AFF_INV = 20
+CAFF_FLOATS = 64 + 3 * (64 * 64 + 64) + 16 * 64 + 16
+
+TC_AVAILABLE = False   # set once csrc/flow_tc.cu carries the tcgen05 conditioner
+
+_MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC}
+
+
+def default_mlp_mode() -> str:
+    return os.environ.get("RNF_MLP_MODE", "fp32")
+
+
+def _np(t: torch.Tensor) -> np.ndarray:
+    return t.detach().to("cpu", torch.float32).contiguous().numpy()
+
+
+def _last_layer_perm(K: int) -> np.ndarray:
+    """Output permutation of fc_last: component c gets columns 4c..4c+3 = (logit_c, w_c.x, w_c.y, w_c.z).
+
+    The reference splits the 4K outputs as [K logits | K x 3 centres] (flow/mobiusflow.py:58-61)."""
+    perm = np.empty(4 * K, dtype=np.int64)
+    for c in range(K):
+        perm[4 * c] = c
+        perm[4 * c + 1: 4 * c + 4] = K + 3 * c + np.arange(3)
+    return perm
+
+
+def pack_mobius(cond_sd: dict, F: int) -> tuple[np.ndarray, np.ndarray | None]:
+    """ConditionalTransform(3+F, 4K) -> (FP32 kernel image [MOB_FLOATS], W_f [64,F] or None)."""
+    W0, b0 = _np(cond_sd["fc_first.weight"]), _np(cond_sd["fc_first.bias"])
+    if W0.shape != (HIDDEN, 3 + F):
+        raise ValueError(f"fc_first.weight has shape {W0.shape}, expected {(HIDDEN, 3 + F)}")
+    blk = np.empty(MOB_FLOATS, dtype=np.float32)
+    first = np.concatenate([W0[:, :3], b0[:, None]], axis=1)            # [64][4]
+    o = 0
+    blk[o:o + 256] = first.reshape(-1); o += 256
+    for j in (1, 3, 5):
+        W, b = _np(cond_sd[f"layers.{j}.weight"]), _np(cond_sd[f"layers.{j}.bias"])
+        blk[o:o + 4096] = W.T.reshape(-1); o += 4096                     # [k][j]
+        blk[o:o + 64] = b; o += 64
+    W4, b4 = _np(cond_sd["fc_last.weight"]), _np(cond_sd["fc_last.bias"])
+    if W4.shape != (4 * K_SEGMENTS, HIDDEN):
+        raise ValueError(f"fc_last.weight has shape {W4.shape}; kernels are built for segments={K_SEGMENTS}")
+    perm = _last_layer_perm(K_SEGMENTS)
+    blk[o:o + 64 * 256] = W4[perm].T.reshape(-1); o += 64 * 256          # [k][j']
+    blk[o:o + 256] = b4[perm]; o += 256
+    assert o == MOB_FLOATS
+    return blk, (np.ascontiguousarray(W0[:, 3:]) if F > 0 else None)
+
+
+def pack_affine_matrix(W: torch.Tensor, is_rot: bool) -> np.ndarray:
+    """One unconditional 4x4 layer -> [W16, log|det W|, pad3, Winv16, log|det Winv|, pad3].
+
+    Forward uses W (flow/squeezetrans.py:167-169); inverse uses torch.linalg.inv(W) (:171-174) and, for rotation
+    layers, the transpose (flow/rottrans.py:26).  Determinants are evaluated in float64 and rounded once."""
+    W64 = W.detach().to("cpu", torch.float64).reshape(4, 4)
+    blk = np.zeros(AFF_FLOATS, dtype=np.float32)
+    blk[:16] = W64.to(torch.float32).reshape(-1).numpy()
+    if is_rot:
+        blk[AFF_INV:AFF_INV + 16] = W64.t().to(torch.float32).reshape(-1).numpy()
+        return blk
+    Winv = torch.linalg.inv(W64)
+    blk[16] = float(torch.linalg.det(W64).abs().log())
+    Winv32 = Winv.to(torch.float32)
+    blk[AFF_INV:AFF_INV + 16] = Winv32.reshape(-1).numpy()
+    blk[AFF_INV + 16] = float(torch.linalg.det(Winv32.double()).abs().log())
+    return blk
+
+
+def pack_cond_affine(net_sd: dict, F: int) -> tuple[np.ndarray, np.ndarray]:
+    """ConditionalTransform(F, 16) -> (tail block [CAFF_FLOATS], W_f [64,F])."""
+    W0, b0 = _np(net_sd["fc_first.weight"]), _np(net_sd["fc_first.bias"])
+    if W0.shape != (HIDDEN, F):
+        raise ValueError(f"net.fc_first.weight has shape {W0.shape}, expected {(HIDDEN, F)}")
+    parts = [b0]
+    for j in (1, 3, 5):
+        parts += [_np(net_sd[f"layers.{j}.weight"]).reshape(-1), _np(net_sd[f"layers.{j}.bias"])]
+    parts += [_np(net_sd["fc_last.weight"]).reshape(-1), _np(net_sd["fc_last.bias"])]
+    blk = np.concatenate(parts).astype(np.float32)
+    assert blk.size == CAFF_FLOATS
+    return blk, W0
+
+
+class LayerSpec:
+    """What the packer needs to know about one layer (produced by the nn.Modules in flow.py)."""
+
+    __slots__ = ("kind", "perm", "module")
+
+    def __init__(self, kind: str, perm: int, module):
+        self.kind = kind      # 'mobius' | 'aff_u' | 'aff_lu' | 'aff_c' | 'rot_u' | 'rot_c'
+        self.perm = perm
+        self.module = module
+
+
+def _sub_sd(module, prefix: str) -> dict:
+    return {k[len(prefix):]: v for k, v in module.state_dict().items() if k.startswith(prefix)}
+
+
+class Program:
+    """A packed layer list bound to one CUDA device (weights + C handle)."""
+
+    def __init__(self, specs: list[LayerSpec], F: int, device: torch.device):
+        self.lib = _cabi.load()
+        self.F = int(F)
+        self.device = device
+        self.n_layers = len(specs)
+        blocks: list[np.ndarray] = []
+        off = 0
+
+        def push(a: np.ndarray) -> int:
+            nonlocal off
+            a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+            pad = (-a.size) % 4
+            if pad:
+                a = np.concatenate([a, np.zeros(pad, np.float32)])
+            blocks.append(a)
+            o = off
+            off += a.size
+            return o
+
+        descs = (_cabi.LayerDesc * max(1, len(specs)))()
+        wf_mob, wf_aff, caff = [], [], []
+        self.rot_slots: list = []          # modules of conditional rotation layers, slot order
+        n_mob = n_aff = 0
+        cond_kinds = set()
+        for i, s in enumerate(specs):
+            d = descs[i]
+            d.perm = int(s.perm) % 3
+            d.cond_slot = -1
+            d.has_ldj = 0
+            d.w_off = 0
+            d.w_off_tc = -1
+            if s.kind == "mobius":
+                d.kind = _cabi.RNF_LAYER_MOBIUS
+                blk, wf = pack_mobius(_sub_sd(s.module, "conditioner."), self.F if s.module.condition else 0)
+                d.w_off = push(blk)
+                if wf is not None:
+                    d.cond_slot = n_mob
+                    n_mob += 1
+                    wf_mob.append(wf)
+            else:
+                d.kind = _cabi.RNF_LAYER_AFFINE
+                d.has_ldj = 0 if s.kind.startswith("rot") else 1
+                if s.kind in ("aff_c", "rot_c"):
+                    cond_kinds.add(s.kind)
+                    blk, wf = pack_cond_affine(_sub_sd(s.module, "net."), self.F)
+                    d.cond_slot = n_aff
+                    n_aff += 1
+                    wf_aff.append(wf)
+                    caff.append(blk)
+                    if s.kind == "rot_c":
+                        self.rot_slots.append(s.module)
+                else:
+                    d.w_off = push(pack_affine_matrix(s.module.matrix(), is_rot=(s.kind == "rot_u")))
+        if len(cond_kinds) > 1:
+            raise NotImplementedError("mixing Condition16Trans and ConditionRot layers in one flow")
+        model = _cabi.ModelDesc()
+        model.abi_version = _cabi.ABI_VERSION
+        model.n_layers = len(specs)
+        model.K, model.H, model.F = K_SEGMENTS, HIDDEN, self.F
+        model.n_mobius_slots, model.n_affine_slots = n_mob, n_aff
+        model.affine_is_rot = 1 if "rot_c" in cond_kinds else 0
+        model.wf_off = push(np.concatenate([w.reshape(-1) for w in wf_mob + wf_aff])) if (wf_mob or wf_aff) else 0
+        model.caff_off = push(np.concatenate(caff)) if caff else 0
+        if not blocks:
+            blocks.append(np.zeros(4, np.float32))
+            off = 4
+        model.n_floats = off
+        self.model = model
+        self.descs = descs
+        self.n_mob, self.n_aff = n_mob, n_aff
+        with torch.cuda.device(device):
+            self.weights = torch.from_numpy(np.concatenate(blocks)).to(device)
+            handle = C.c_void_p()
+            _cabi.check(self.lib.rnf_flow_create(C.byref(model), descs, C.c_void_p(self.weights.data_ptr()), C.byref(handle)))
+        self.handle = handle
+        self.cond_floats = int(self.lib.rnf_flow_cond_floats(handle))
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            try:
+                self.lib.rnf_flow_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    # ------------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def condition(self, feat: torch.Tensor) -> torch.Tensor:
+        """feat [B,F] -> per-image constants [B, cond_floats] (rnf_flow_condition)."""
+        B = feat.shape[0]
+        feat = feat.to(self.device, torch.float32).contiguous()
+        if feat.dim() != 2 or feat.shape[1] != self.F:
+            raise ValueError(f"feature must be [B,{self.F}], got {tuple(feat.shape)}")
+        cond = torch.empty((B, self.cond_floats), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.rnf_flow_condition(self.handle, C.c_void_p(feat.data_ptr()), B,
+                                                    C.c_void_p(cond.data_ptr()), self._stream()))
+        if self.rot_slots:
+            # ConditionRot (flow/rottrans.py:43-46,55-58): rot = U^T V with (U,S,V) = torch.svd(MLP(feature)+I);
+            # the SVD stays the very library call the reference makes (its sign convention defines the layer).
+            base = self.n_mob * HIDDEN
+            blk = cond[:, base: base + self.n_aff * AFF_FLOATS].view(B, self.n_aff, AFF_FLOATS)
+            M = blk[:, :, :16].reshape(B, self.n_aff, 4, 4)
+            # U^T V is NOT invariant under the sign freedom of an SVD (it maps to D U^T V D), so the LAPACK routine behind
+            # CPU torch.svd -- the one the golden vectors were minted with -- is used for determinism.
+            U, _, V = torch.svd(M.cpu())
+            rot = (U.transpose(-1, -2) @ V).to(M.device)
+            blk[:, :, :16] = rot.reshape(B, self.n_aff, 16)
+            blk[:, :, AFF_INV:AFF_INV + 16] = rot.transpose(-1, -2).reshape(B, self.n_aff, 16)
+        return cond
+
+    def run(self, R: torch.Tensor, cond, B: int, feat_index, rows_per_image: int, inverse: bool, mode: str):
+        N = R.shape[0]
+        R_out = torch.empty((N, 3, 3), device=self.device, dtype=torch.float32)
+        ldj = torch.empty((N,), device=self.device, dtype=torch.float32)
+        if N == 0:
+            return R_out, ldj
+        cp = C.c_void_p(cond.data_ptr()) if cond is not None else None
+        ip = C.c_void_p(feat_index.data_ptr()) if feat_index is not None else None
+        m = _MODES[mode]
+        with torch.cuda.device(self.device):
+            if inverse:
+                ns = int(self.lib.rnf_flow_inverse_scratch_floats(self.handle, N))
+                scratch = torch.empty((max(ns, 1),), device=self.device, dtype=torch.float32)
+                _cabi.check(self.lib.rnf_flow_inverse(self.handle, C.c_void_p(R.data_ptr()), N, cp, B, ip, rows_per_image,
+                                                      C.c_void_p(R_out.data_ptr()), C.c_void_p(ldj.data_ptr()),
+                                                      C.c_void_p(scratch.data_ptr()), m, self._stream()))
+            else:
+                _cabi.check(self.lib.rnf_flow_forward(self.handle, C.c_void_p(R.data_ptr()), N, cp, B, ip, rows_per_image,
+                                                      C.c_void_p(R_out.data_ptr()), C.c_void_p(ldj.data_ptr()), m,
+                                                      self._stream()))
+        return R_out, ldj
+
+    def grid_logprob(self, grid: torch.Tensor, g_index0: int, offset, cond, B: int, fisher_A, fisher_c,
+                     want_logp: bool, mode: str):
+        G = grid.shape[0]
+        dev = self.device
+        mx = torch.empty((B,), device=dev, dtype=torch.float32)
+        am = torch.empty((B,), device=dev, dtype=torch.int64)
+        se = torch.empty((B,), device=dev, dtype=torch.float32)
+        logp = torch.empty((B, G), device=dev, dtype=torch.float32) if want_logp else None
+        part = torch.empty((max(1, int(self.lib.rnf_grid_partial_floats(G, B))),), device=dev, dtype=torch.float32)
+        vp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        with torch.cuda.device(dev):
+            _cabi.check(self.lib.rnf_grid_logprob(self.handle, vp(grid), G, int(g_index0), vp(offset), vp(cond), B,
+                                                  vp(fisher_A), vp(fisher_c), vp(logp), vp(part), vp(mx), vp(am), vp(se),
+                                                  _MODES[mode], self._stream()))
+        return mx, am, se, logp
+
+
+def dedup_rows(feature: torch.Tensor):
+    """Row-aligned ``feature [N,F]`` (built by ``.repeat`` at agent.py:240-244 / eval.py:450) ->
+    (unique consecutive rows [B,F], int32 row->image index [N] or None, rows_per_image)."""
+    N = feature.shape[0]
+    if N == 0:
+        return feature, None, 1
+    if feature.stride(0) == 0 or N == 1:
+        return feature[:1].contiguous(), None, N
+    neq = (feature[1:] != feature[:-1]).any(dim=1)
+    idx = torch.zeros(N, dtype=torch.int32, device=feature.device)
+    idx[1:] = torch.cumsum(neq, 0, dtype=torch.int32)
+    B = int(idx[-1].item()) + 1
+    if B == 1:
+        return feature[:1].contiguous(), None, N
+    first = torch.cat([torch.zeros(1, dtype=torch.int64, device=feature.device), torch.nonzero(neq).squeeze(1) + 1])
+    return feature[first].contiguous(), idx, 0

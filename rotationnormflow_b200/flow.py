@@ -1,0 +1,403 @@
+"""Drop-in replacement for the reference's ``flow/flow.py`` (and the layer classes it instantiates).
+
+Same public surface, same constructor semantics, same ``state_dict`` keys -- checkpoints written by
+``Agent.save_ckpt`` (agent.py:111-153, key ``flow_state_dict``) load with ``load_state_dict``:
+
+    get_flow(config) -> Flow                                             flow/flow.py:9-10
+    Flow.forward(rotation, feature=None, inverse=False, draw=False)      flow/flow.py:53-72
+    Flow.inverse(rotation, feature=None, draw=False)                     flow/flow.py:74-92
+    layer(rotation, permute, feature) / layer.inverse(...)               per-layer protocol of flow/*.py
+
+but every call runs as ONE fused CUDA kernel over the whole layer stack (csrc/flow_v1.cu, csrc/flow_tc.cu)
+instead of ~6.5 k (forward) / ~22 k (inverse) ATen launches.  The modules below only hold parameters; they
+contain no per-rotation PyTorch arithmetic and there is no CPU path: tensors must live on a B200.
+
+Additions that the reference does not have (N1 in SURVEY.md section 8f):
+    Flow.forward(..., feature_index=idx)   features given once per image [B,F] plus a row->image index
+    Flow.grid_log_prob(grid, feature, ...) fused log-prob / arg-max / normaliser over a rotation grid
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import engine
+
+_PERMUTE_ROWS = ((0, 1, 2), (1, 2, 0), (2, 0, 1), (0, 1, 2), (1, 2, 0), (2, 0, 1))   # flow/flow.py:13-15
+
+
+def get_flow(config):
+    return Flow(config)
+
+
+# ------------------------------------------------------------------------------------------------------
+# parameter containers (state-dict compatible with the reference modules)
+# ------------------------------------------------------------------------------------------------------
+class ConditionalTransform(nn.Module):
+    """Parameters of the 4-layer residual ReLU MLP of flow/condition.py:4-30 (Ni -> 64 -> 64 -> 64 -> 64 -> No).
+
+    Keys: fc_first.{weight,bias}, layers.{1,3,5}.{weight,bias}, fc_last.{weight,bias}.  Creation order matches the
+    reference so that a seeded construction draws identical initial weights."""
+
+    def __init__(self, Ni: int, No: int, Nh: int = 64):
+        super().__init__()
+        self.fc_first = nn.Linear(Ni, Nh)
+        hidden = []
+        for _ in range(3):
+            hidden += [nn.ReLU(), nn.Linear(Nh, Nh)]
+        self.relu_last = nn.ReLU()
+        self.fc_last = nn.Linear(Nh, No)
+        self.layers = nn.ModuleList(hidden)
+
+    def forward(self, x):  # pragma: no cover - deliberately not a compute path
+        raise RuntimeError("ConditionalTransform is evaluated inside the fused CUDA kernels; call the owning layer / Flow")
+
+
+class _FusedLayer(nn.Module):
+    """Common per-layer protocol: ``layer(rotation, permute, feature)`` and ``layer.inverse(...)``."""
+
+    kind = ""
+    uses_feature = False
+
+    def _feature_dim(self) -> int:
+        return 0
+
+    def forward(self, rotation, permute=None, feature=None):
+        return _run([self], [_perm_row(permute, self)], self._feature_dim(), self, rotation, feature, False)
+
+    def inverse(self, rotation, permute=None, feature=None):
+        return _run([self], [_perm_row(permute, self)], self._feature_dim(), self, rotation, feature, True)
+
+
+class MobiusFlow(_FusedLayer):
+    """flow/mobiusflow.py:27-183.  ``conditioner`` = ConditionalTransform(D + feature_dim, 4K)."""
+
+    kind = "mobius"
+
+    def __init__(self, D, K, condition=0, feature_dim=None):
+        super().__init__()
+        if D != 3:
+            raise ValueError("MobiusFlow acts on columns of a 3x3 rotation: D must be 3")
+        if K != engine.K_SEGMENTS:
+            raise NotImplementedError(f"the sm_100a kernels are specialised for segments={engine.K_SEGMENTS} (every settings/*.yml); got {K}")
+        self.D, self.K = D, K
+        self.condition = condition
+        self.feature_dim = feature_dim
+        self.uses_feature = bool(condition)
+        self.conditioner = ConditionalTransform(D + (feature_dim if condition else 0), 4 * K)
+
+    def _feature_dim(self):
+        return self.feature_dim if self.condition else 0
+
+    def forward(self, rotation, permute=None, feature=None):
+        assert permute is not None, "The permuting function is needed in this module"
+        if self.condition:
+            assert feature is not None, "The input feature is needed in this module"
+        return super().forward(rotation, permute, feature if self.condition else None)
+
+    def inverse(self, rotation, permute=None, feature=None):
+        assert permute is not None, "The permuting function is needed in this module"
+        if self.condition:
+            assert feature is not None, "feature input is needed in this module"
+        return super().inverse(rotation, permute, feature if self.condition else None)
+
+
+class Uncondition16Trans(_FusedLayer):
+    """flow/squeezetrans.py:161-174: a free 4x4 matrix acting on the quaternion."""
+
+    kind = "aff_u"
+
+    def __init__(self):
+        super().__init__()
+        self.mat = nn.Parameter(torch.eye(4).unsqueeze(0) + torch.randn(1, 4, 4) * 1e-3)
+
+    def matrix(self):
+        return self.mat
+
+
+class UnconditionLU(nn.Module):
+    """flow/squeezetrans.py:58-91: PLU parameterisation W = P (L*lmask + I) (U*umask + diag(sign*exp(s)))."""
+
+    def __init__(self, in_channel: int):
+        super().__init__()
+        from scipy import linalg as la
+        w0 = 1e-3 * np.random.randn(in_channel, in_channel) + np.eye(in_channel)
+        q, _ = la.qr(w0)
+        p, l, u = la.lu(q.astype(np.float32))
+        s = np.diag(u)
+        u = np.triu(u, 1)
+        um = np.triu(np.ones_like(u), 1)
+        self.register_buffer("w_p", torch.from_numpy(p))
+        self.register_buffer("u_mask", torch.from_numpy(um))
+        self.register_buffer("l_mask", torch.from_numpy(um.T.copy()))
+        s_t = torch.from_numpy(np.copy(s))
+        self.register_buffer("s_sign", torch.sign(s_t))
+        self.register_buffer("l_eye", torch.eye(in_channel))
+        self.w_l = nn.Parameter(torch.from_numpy(l))
+        self.w_s = nn.Parameter(s_t.abs().log())
+        self.w_u = nn.Parameter(torch.from_numpy(u))
+
+    def forward(self):
+        """Parameter algebra on one 4x4 (not a per-rotation path): returns W [1,4,4]."""
+        low = self.w_l * self.l_mask + self.l_eye
+        up = self.w_u * self.u_mask + torch.diag(self.s_sign * torch.exp(self.w_s))
+        return (self.w_p @ low @ up).unsqueeze(0)
+
+
+class Uncondition16TransLU(_FusedLayer):
+    """flow/squeezetrans.py:147-158."""
+
+    kind = "aff_lu"
+
+    def __init__(self):
+        super().__init__()
+        self.mat = UnconditionLU(4)
+
+    def matrix(self):
+        with torch.no_grad():
+            return self.mat()
+
+
+class Condition16Trans(_FusedLayer):
+    """flow/squeezetrans.py:41-55: W = MLP(feature).reshape(4,4) + I, evaluated once per image on device."""
+
+    kind = "aff_c"
+    uses_feature = True
+
+    def __init__(self, feature_dim):
+        super().__init__()
+        self.feature_dim = feature_dim
+        self.net = ConditionalTransform(feature_dim, 16)
+
+    def _feature_dim(self):
+        return self.feature_dim
+
+
+class UnconditionRot(_FusedLayer):
+    """flow/rottrans.py:8-35: 4-D rotation U^T V from torch.svd of a free 4x4; log-det 0."""
+
+    kind = "rot_u"
+
+    def __init__(self):
+        super().__init__()
+        self.rot = nn.Parameter(torch.randn((1, 4, 4)) * 1e-3 + torch.eye(4).unsqueeze(0))
+
+    def matrix(self):
+        with torch.no_grad():
+            U, _, V = torch.svd(self.rot.detach().to("cpu"))
+            return U.transpose(-1, -2) @ V
+
+
+class ConditionRot(_FusedLayer):
+    """flow/rottrans.py:38-66."""
+
+    kind = "rot_c"
+    uses_feature = True
+
+    def __init__(self, feature_dim):
+        super().__init__()
+        self.feature_dim = feature_dim
+        self.net = ConditionalTransform(feature_dim, 16)
+
+    def _feature_dim(self):
+        return self.feature_dim
+
+
+_OUT_OF_SCOPE = {
+    "36Trans": "Condition36Trans/Uncondition36Trans (flow/squeezetrans.py:200-361)",
+    "9TransLSVD": "Condition9RotL/Uncondition9RotL (flow/rottrans.py:69-181)",
+    "9TransRSVD": "Condition9RotR/Uncondition9RotR (flow/rottrans.py:69-181)",
+    "9TransLSmith": "Condition9Trans/Uncondition9Trans (flow/squeezetrans.py:177-361)",
+    "9TransRSmith": "Condition9RotRSmith/Uncondition9RotRSmith (flow/rottrans.py:69-181)",
+}
+
+
+def get_mobius(config, feature_dim):
+    """flow/mobiusflow.py:7-14."""
+    if config.dist == "noflow":
+        return None
+    return MobiusFlow(3, config.segments, condition=config.condition, feature_dim=feature_dim)
+
+
+def get_affine(config, feature_dim, first_layer_condition=False):
+    """Dispatch table of flow/affineflow.py:5-73 for the layer families on the hot path."""
+    rot, lu = config.rot, bool(getattr(config, "lu", 0))
+
+    def lu_conditional():
+        raise NotImplementedError(
+            "Condition16TransLU (flow/squeezetrans.py:94-144) is batch-coupled in the reference (torch.diag on a [N,4] "
+            "tensor) and is outside the hot-path scope (SURVEY.md section 2 row 5)")
+
+    if first_layer_condition:
+        if rot == "16UnTrans":
+            return lu_conditional() if lu else Condition16Trans(feature_dim)
+        if rot == "16UnRot":
+            return ConditionRot(feature_dim)
+    if rot in _OUT_OF_SCOPE:
+        raise NotImplementedError(f"rot={rot!r}: {_OUT_OF_SCOPE[rot]} is an ablation layer outside the hot-path scope (SURVEY.md 8f N4)")
+    if config.condition:
+        if rot == "16Trans":
+            return lu_conditional() if lu else Condition16Trans(feature_dim)
+        if rot == "16UnTrans":
+            return Uncondition16TransLU() if lu else Uncondition16Trans()
+        if rot == "16Rot":
+            return ConditionRot(feature_dim)
+        if rot == "16UnRot":
+            return UnconditionRot()
+        return None
+    if rot == "16Trans":
+        return Uncondition16TransLU() if lu else Uncondition16Trans()
+    if rot == "16Rot":
+        return UnconditionRot()
+    return None
+
+
+# ------------------------------------------------------------------------------------------------------
+# execution plumbing
+# ------------------------------------------------------------------------------------------------------
+def _perm_row(permute, layer) -> int:
+    if permute is None:
+        return 0
+    p = [int(v) for v in (permute.tolist() if torch.is_tensor(permute) else permute)]
+    if len(p) != 3 or sorted(p) != [0, 1, 2] or (p[1] - p[0]) % 3 != 1 or (p[2] - p[1]) % 3 != 1:
+        raise NotImplementedError(f"permute={p}: only the cyclic rows of flow/flow.py:13-15 exist in the reference")
+    return p[0]
+
+
+def _signature(layers) -> tuple:
+    sig = []
+    for l in layers:
+        for t in list(l.parameters()) + list(l.buffers()):
+            sig.append((t.data_ptr(), t._version))
+    return tuple(sig)
+
+
+def _program(owner, layers, perms, F, device) -> engine.Program:
+    cache = owner.__dict__.setdefault("_rnf_programs", {})
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tuple(perms))
+    sig = _signature(layers)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == sig:
+        return hit[1]
+    specs = [engine.LayerSpec(l.kind, p, l) for l, p in zip(layers, perms)]
+    prog = engine.Program(specs, F, torch.device("cuda", key[0]))
+    cache[key] = (sig, prog)
+    return prog
+
+
+def _check_rotation(rotation):
+    if not torch.is_tensor(rotation) or rotation.dim() != 3 or tuple(rotation.shape[1:]) != (3, 3):
+        raise ValueError(f"rotation must be a [N,3,3] tensor, got {tuple(getattr(rotation, 'shape', ()))}")
+    if not rotation.is_cuda:
+        raise RuntimeError("rotationnormflow_b200 runs on a B200 only: `rotation` must be a CUDA tensor (there is no CPU fallback)")
+    if rotation.requires_grad:
+        raise NotImplementedError("autograd through the fused kernels is outside the hot-path scope (inference / evaluation only)")
+    return rotation.to(torch.float32).contiguous()
+
+
+def _run(layers, perms, F, owner, rotation, feature, inverse, feature_index=None, mode=None):
+    R = _check_rotation(rotation)
+    prog = _program(owner, layers, perms, F, R.device)
+    mode = mode or engine.default_mlp_mode()
+    N = R.shape[0]
+    if prog.cond_floats == 0:
+        return prog.run(R, None, 0, None, 1, inverse, mode)
+    if feature is None:
+        raise AssertionError("The input feature is needed in this module")
+    feature = feature.to(R.device)
+    if feature_index is not None:
+        idx = feature_index.to(R.device, torch.int32).contiguous()
+        if idx.shape[0] != N:
+            raise ValueError("feature_index must have one entry per rotation")
+        return prog.run(R, prog.condition(feature), feature.shape[0], idx, 0, inverse, mode)
+    if feature.shape[0] != N:
+        raise ValueError(f"feature has {feature.shape[0]} rows for {N} rotations (the reference asserts equality, agent.py:211,259)")
+    # bound the per-image constant buffer when every row carries its own feature
+    max_rows = max(1, (1 << 28) // max(1, prog.cond_floats))
+    if N <= max_rows:
+        uniq, idx, rpi = engine.dedup_rows(feature)
+        return prog.run(R, prog.condition(uniq), uniq.shape[0], idx, rpi, inverse, mode)
+    outs = []
+    for s in range(0, N, max_rows):
+        uniq, idx, rpi = engine.dedup_rows(feature[s:s + max_rows])
+        outs.append(prog.run(R[s:s + max_rows], prog.condition(uniq), uniq.shape[0], idx, rpi, inverse, mode))
+    return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+
+
+class Flow(nn.Module):
+    """flow/flow.py:18-92."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.condition = config.condition
+        self._permute = torch.tensor(_PERMUTE_ROWS, dtype=torch.long)
+        if self.condition:
+            self.feature_dim = 32 if config.feature_dim is None else config.feature_dim
+            if config.embedding:
+                self.feature_dim += config.embedding_dim
+        else:
+            self.feature_dim = 0
+        n = config.layers
+        stack = []
+        if getattr(config, "last_affine", 0):
+            stack.append(get_affine(config, self.feature_dim, first_layer_condition=True))
+        for i in range(n):
+            m = get_mobius(config, self.feature_dim)
+            if m is not None:
+                stack.append(m)
+            a = get_affine(config, self.feature_dim)
+            if a is not None and (i != n - 1 or getattr(config, "first_affine", 1)):
+                stack.append(a)
+        print("total layers of flow: ", len(stack))
+        self.layers = nn.ModuleList(stack)
+
+    # permutation row handed to layer i in either direction (flow/flow.py:58-70 and :78-88 agree layer by layer)
+    def _perm_rows(self):
+        rows, c = [], 0
+        freq = bool(getattr(self.config, "frequent_permute", 0))
+        for l in self.layers:
+            rows.append(_PERMUTE_ROWS[c % 6][0])
+            if isinstance(l, MobiusFlow) or freq:
+                c += 1
+        return rows
+
+    def forward(self, rotation, feature=None, inverse=False, draw=False, feature_index=None, mlp_mode=None):
+        if not self.condition:
+            feature = None
+        return _run(list(self.layers), self._perm_rows(), self.feature_dim, self, rotation, feature, bool(inverse),
+                    feature_index, mlp_mode)
+
+    def inverse(self, rotation, feature=None, draw=False, feature_index=None, mlp_mode=None):
+        return self.forward(rotation, feature, True, draw, feature_index, mlp_mode)
+
+    # ---- N1: the loops of eval.py:444-462 / agent.py:246-266 as one call -------------------
+    def grid_log_prob(self, grid, feature=None, offset=None, fisher_A=None, return_logp=False, g_index0=0, mlp_mode=None):
+        """log p(grid[g] @ offset | image b) for all b, g, reduced per image on the fly.
+
+        grid [G,3,3] (this rank's slice; ``g_index0`` = global index of grid[0]); feature [B,F] one row per image
+        (None for an unconditional flow -> B = 1); fisher_A [B,3,3] adds the matrix-Fisher base term
+        (utils/fisher.py:217-232, image-major as at agent.py:246-251).
+        Returns dict(max [B], argmax [B] int64 global grid index (first on ties), sumexp [B] = sum_g exp(logp - max),
+        logp [B,G] if requested)."""
+        from .fisher import fisher_constants
+        G_ = _check_rotation(grid)
+        prog = _program(self, list(self.layers), self._perm_rows(), self.feature_dim, G_.device)
+        cond, B = None, 1
+        if prog.cond_floats:
+            if feature is None:
+                raise AssertionError("The input feature is needed in this module")
+            cond = prog.condition(feature.to(G_.device))
+            B = feature.shape[0]
+        A9 = c = None
+        if fisher_A is not None:
+            A9, c = fisher_constants(fisher_A.to(G_.device))
+            if A9.shape[0] != B:
+                raise ValueError("fisher_A must have one 3x3 matrix per image")
+        off = None if offset is None else offset.to(G_.device, torch.float32).contiguous()
+        mx, am, se, logp = prog.grid_logprob(G_, g_index0, off, cond, B, A9, c, return_logp, mlp_mode or engine.default_mlp_mode())
+        out = dict(max=mx, argmax=am, sumexp=se)
+        if return_logp:
+            out["logp"] = logp
+        return out

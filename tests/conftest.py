@@ -1,0 +1,88 @@
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+SMALL_CASES = ["s_uncond", "s_symsol", "s_modelnet", "s_pascal", "s_lu", "s_rot", "s_rotc", "s_unrot", "s_mobonly"]
+FULL_CASES = ["raw", "symsol2048", "symsol2", "modelnet"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
+class Golden:
+    def __init__(self, tag):
+        self.tag = tag
+        self.z = np.load(os.path.join(GOLDEN, f"flow_{tag}.npz"), allow_pickle=False)
+        self.cfg = types.SimpleNamespace(**json.loads(str(self.z["cfg"])))
+        self.seed = int(self.z["seed"])
+        self.R = torch.from_numpy(self.z["R"])
+        self.has_feat = "feat" in self.z.files
+        self.feat = torch.from_numpy(self.z["feat"]) if self.has_feat else None
+        self.feat_index = torch.from_numpy(self.z["feat_index"].astype(np.int64)) if self.has_feat else None
+        self.sd_keys = [(k, tuple(s)) for k, s in json.loads(str(self.z["sd_keys"]))]
+        self.sd_checksum = float(self.z["sd_checksum"])
+
+    @property
+    def rows(self):
+        return None if self.feat is None else self.feat[self.feat_index]
+
+    def out(self, direction, what, prec):
+        return torch.from_numpy(self.z[f"{direction}_{what}_{prec}"])
+
+    def stored_state_dict(self):
+        sd = {k[4:]: torch.from_numpy(self.z[k]) for k in self.z.files if k.startswith("sd::")}
+        return sd or None
+
+    def state_dict(self):
+        """Stored weights (small cases) or weights regenerated from the seed through the product module, whose
+        parameter-creation order mirrors the reference (checked against the stored checksum)."""
+        sd = self.stored_state_dict()
+        if sd is not None:
+            return sd
+        return seeded_product_flow(self.cfg, self.seed).state_dict()
+
+
+def sd_checksum(sd):
+    tot = 0.0
+    for i, (k, v) in enumerate(sorted(sd.items())):
+        tot += float(v.double().abs().sum()) * (1 + (i % 7))
+    return tot
+
+
+def seeded_product_flow(cfg, seed):
+    import contextlib
+    import io
+    import rotationnormflow_b200 as rnf
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        return rnf.get_flow(cfg)
+
+
+_cache = {}
+
+
+def golden(tag):
+    if tag not in _cache:
+        _cache[tag] = Golden(tag)
+    return _cache[tag]

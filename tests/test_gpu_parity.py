@@ -1,0 +1,279 @@
+"""Parity of the CUDA path (through the drop-in module -> ctypes -> C ABI -> kernels) against the golden vectors of the
+real reference and against the CPU oracle.  Run on the B200 box:  python -m pytest tests -m gpu
+
+Tolerances (BASELINE.json north_star): rotations within 1e-5 max-abs, log-probs within 1e-4 relative
+(|d| / max(|ref|, 1): ldj crosses zero), grid indices / arg-max bit-exact (ties: see test_grid_*).
+For the F=2080 ModelNet configuration the reference's own fp32-vs-fp64 gap is 4.5e-5 / 6.2e-5,
+so that case is held to 1e-4 max-abs against the fp64 reference output instead.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import FULL_CASES, GOLDEN, SMALL_CASES, golden, seeded_product_flow
+from oracle import rnf_oracle as orc
+import rotationnormflow_b200 as rnf
+from rotationnormflow_b200 import grid as rgrid
+from rotationnormflow_b200.fisher import fisher_constants
+
+pytestmark = pytest.mark.gpu
+
+MODES = [m for m in os.environ.get("RNF_TEST_MODES", "fp32,tc").split(",") if m]
+
+
+def _mode_available(mode):
+    if mode == "fp32":
+        return True
+    from rotationnormflow_b200 import engine
+    return getattr(engine, "TC_AVAILABLE", False)
+
+
+def _product(g, dev="cuda"):
+    m = seeded_product_flow(g.cfg, g.seed)
+    sd = g.stored_state_dict()
+    if sd is not None:
+        m.load_state_dict(sd)
+    return m.to(dev).eval()
+
+
+def rel(a, ref):
+    return ((a - ref).abs() / ref.abs().clamp(min=1.0)).max().item()
+
+
+R_TOL = {"modelnet": 1e-4}
+LDJ_TOL = {"modelnet": 2e-4}
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("tag", SMALL_CASES + FULL_CASES)
+def test_forward_parity(tag, mode):
+    if not _mode_available(mode):
+        pytest.skip("tensor-core conditioner not built in this revision")
+    g = golden(tag)
+    m = _product(g)
+    feat = None if g.rows is None else g.rows.cuda()
+    with torch.no_grad():
+        R, ldj = m(g.R.cuda(), feat, mlp_mode=mode)
+    R, ldj = R.cpu().double(), ldj.cpu().double()
+    dR64 = (R - g.out("fwd", "R", "f64")).abs().max().item()
+    dl64 = rel(ldj, g.out("fwd", "ldj", "f64"))
+    dR32 = (R - g.out("fwd", "R", "f32").double()).abs().max().item()
+    print(f"\n[{tag}/{mode}] fwd  max|dR| vs ref-fp64 {dR64:.2e}  vs ref-fp32 {dR32:.2e}   rel dldj vs ref-fp64 {dl64:.2e}")
+    assert dR64 <= R_TOL.get(tag, 1e-5)
+    assert dl64 <= LDJ_TOL.get(tag, 1e-4)
+    # outputs stay rotations
+    assert (R @ R.transpose(1, 2) - torch.eye(3, dtype=torch.float64)).abs().max() < 5e-6
+    # the same call with features given once per image + a row index
+    if feat is not None:
+        with torch.no_grad():
+            R2, l2 = m(g.R.cuda(), g.feat.cuda(), feature_index=g.feat_index.cuda(), mlp_mode=mode)
+        assert torch.equal(R2.cpu().double(), R) and torch.equal(l2.cpu().double(), ldj)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("tag", SMALL_CASES + FULL_CASES)
+def test_inverse_parity(tag, mode):
+    if not _mode_available(mode):
+        pytest.skip("tensor-core conditioner not built in this revision")
+    g = golden(tag)
+    m = _product(g)
+    feat = None if g.rows is None else g.rows.cuda()
+    with torch.no_grad():
+        R, ldj = m.inverse(g.R.cuda(), feat, mlp_mode=mode)
+        Rf, lf = m(R, feat, mlp_mode=mode)
+    nmob = sum(l.kind == "mobius" for l in m.layers)
+    Rc, lc = R.cpu().double(), ldj.cpu().double()
+    ref32, ref64 = g.out("inv", "R", "f32").double(), g.out("inv", "R", "f64")
+    d32 = (Rc - ref32).abs().amax(dim=(1, 2))
+    d64 = (Rc - ref64).abs().amax(dim=(1, 2))
+    own = (ref32 - ref64).abs().amax(dim=(1, 2))           # the reference's own fp32-vs-fp64 flips
+    frac32 = (d32 <= 1e-5).float().mean().item()
+    frac64 = (d64 <= 1e-5).float().mean().item()
+    frac_own = (own <= 1e-5).float().mean().item()
+    print(f"\n[{tag}/{mode}] inv  rows within 1e-5: vs ref-fp32 {frac32:.3f}  vs ref-fp64 {frac64:.3f}  (ref fp32 vs ref fp64: {frac_own:.3f})"
+          f"  worst {d64.max().item():.2e}")
+    # Bisection returns a dyadic angle of resolution pi/2^15; one-ulp noise at a probe flips a branch and moves the
+    # row by up to 1.9e-4 per Mobius layer.  Bound: as many exact rows as the reference's own
+    # fp32 run (minus slack), and no row further than the flip bound.
+    assert frac64 >= min(frac_own, 0.97) - 0.05
+    assert d64.max().item() <= max(2e-4 * nmob, 1e-5)
+    # size-independent properties: forward(inverse(z)) ~ z to bisection resolution, ldj_inv = -ldj_fwd
+    assert (Rf.cpu().double() - g.R.double()).abs().max().item() <= max(2e-4 * nmob, 1e-5)
+    assert (lf.cpu().double() + lc).abs().max().item() <= max(2e-3 * nmob, 1e-5)
+    l64 = g.out("inv", "ldj", "f64")
+    ok = d64 <= 1e-5
+    if ok.any():
+        assert rel(lc[ok], l64[ok]) <= 2e-4
+
+
+@pytest.mark.parametrize("tag", ["s_uncond", "s_symsol", "s_modelnet", "s_rotc", "s_lu"])
+def test_single_layer_protocol(tag):
+    """layer(rotation, permute, feature) / layer.inverse(...) -- the per-layer protocol of flow/*.py -- against the oracle."""
+    g = golden(tag)
+    m = _product(g)
+    o = orc.OracleFlow(g.cfg, g.state_dict(), torch.float64)
+    rows = orc.permute_rows(g.cfg, o.plan)
+    feat = None if g.rows is None else g.rows
+    R = g.R
+    for i, layer in enumerate(m.layers):
+        p = orc.PERMUTE_TABLE[rows[i]]
+        perm = torch.tensor(p, dtype=torch.long, device="cuda")
+        f_i = feat.cuda() if (feat is not None and layer.uses_feature) else None
+        with torch.no_grad():
+            Rg, lg = layer(R.cuda(), perm, f_i)
+        kind, pre = o.plan[i], f"layers.{i}."
+        f64 = None if feat is None else feat.double()
+        if kind == "mobius":
+            Ro, lo = orc.mobius_forward(o.sd, pre, R.double(), p, f64, 64)
+        else:
+            W, has = orc.affine_matrix(o.sd, pre, kind, f64, False)
+            Ro, lo = orc.quat_affine(W, R.double(), has)
+        assert (Rg.cpu().double() - Ro).abs().max() < 3e-6, (i, kind)
+        assert (lg.cpu().double() - lo).abs().max() < 1e-5, (i, kind)
+        R = Ro.float()
+
+
+def test_edge_cases():
+    g = golden("s_symsol")
+    m = _product(g)
+    F = g.feat.shape[1]
+    with torch.no_grad():
+        R0, l0 = m(torch.empty(0, 3, 3, device="cuda"), torch.empty(0, F, device="cuda"))
+        assert R0.shape == (0, 3, 3) and l0.shape == (0,)
+        # ragged: 1 row, 255/256/257 rows (tile boundary), each row its own feature
+        for n in (1, 127, 128, 129, 255, 256, 257):
+            R = g.R[:n].cuda()
+            f = g.rows[:n].cuda()
+            Rn, ln = m(R, f)
+            Rall, lall = m(g.R.cuda(), g.rows.cuda())
+            assert torch.equal(Rn, Rall[:n]) and torch.equal(ln, lall[:n])
+        # every row a distinct image
+        f = torch.relu(torch.randn(64, F, generator=torch.Generator().manual_seed(0))).cuda()
+        Rn, ln = m(g.R[:64].cuda(), f)
+        o = orc.OracleFlow(g.cfg, g.state_dict(), torch.float64)
+        Ro, lo = o.forward(g.R[:64], f.cpu())
+        assert (Rn.cpu().double() - Ro).abs().max() < 1e-5 and rel(ln.cpu().double(), lo) < 1e-4
+        # inputs are not modified, non-contiguous input accepted
+        Rin = g.R.cuda()
+        keep = Rin.clone()
+        m(Rin, g.rows.cuda())
+        assert torch.equal(Rin, keep)
+        Rt = g.R.cuda().transpose(1, 2).contiguous().transpose(1, 2)
+        assert torch.equal(m(Rt, g.rows.cuda())[0], m(g.R.cuda(), g.rows.cuda())[0])
+    with pytest.raises(AssertionError):
+        m(g.R.cuda(), None)
+    with pytest.raises(ValueError):
+        m(g.R.cuda(), g.rows[:5].cuda())
+    # checkpoint-style weight update is picked up (load_state_dict bumps parameter versions)
+    with torch.no_grad():
+        before = m(g.R.cuda(), g.rows.cuda())[1].clone()
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        sd["layers.1.conditioner.fc_last.bias"] += 0.25
+        m.load_state_dict(sd)
+        after = m(g.R.cuda(), g.rows.cuda())[1]
+    assert (before - after).abs().max() > 1e-4
+
+
+def test_healpix_grid_on_device():
+    z = np.load(f"{GOLDEN}/healpix_grid.npz")
+    for level in (0, 1, 2):
+        G = rgrid.healpix_grid(level).cpu().numpy()
+        ref = z[f"full_{level}"]
+        assert G.shape == ref.shape
+        assert np.abs(G - ref).max() <= 1.2e-7
+        big = np.abs(ref) > 1e-9
+        assert (G[big] != ref[big]).mean() < 1e-3
+    for level in (3, 4):
+        idx = z[f"idx_{level}"]
+        G = rgrid.healpix_grid(level).cpu().numpy()
+        assert np.abs(G[idx] - z[f"sample_{level}"]).max() <= 1.2e-7
+        b = int(idx[7])
+        assert np.array_equal(rgrid.healpix_grid(level, b, b + 1000).cpu().numpy(), G[b:b + 1000])
+    # full BASELINE size (level 5, 2 359 296 rotations): orthonormal, det +1, matches the CPU oracle on a slice
+    G5 = rgrid.healpix_grid(5)
+    assert G5.shape == (2_359_296, 3, 3)
+    Gd = G5.double()
+    assert (Gd @ Gd.transpose(1, 2) - torch.eye(3, device="cuda", dtype=torch.float64)).abs().max() < 1e-6
+    assert (torch.linalg.det(Gd) - 1).abs().max() < 1e-6
+    sl = orc.healpix_grid(5, 1_234_567, 1_234_567 + 5000)
+    assert (G5[1_234_567:1_234_567 + 5000].cpu() - sl).abs().max() <= 1.2e-7
+    assert rgrid.generate_queries(2_400_000, "grid").shape[0] == 2_359_296
+    assert rgrid.closest_grid_level(37_000_000) == 6
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("tag", ["s_symsol", "s_modelnet", "s_uncond"])
+def test_grid_log_prob(tag, mode):
+    """Fused grid evaluation == forward + Fisher base + torch reductions, and == the oracle on the same inputs."""
+    if not _mode_available(mode):
+        pytest.skip("tensor-core conditioner not built in this revision")
+    g = golden(tag)
+    m = _product(g)
+    grid = rgrid.healpix_grid(2)                           # 4608 rotations: not a multiple of the tile sizes? (4608 = 18*256)
+    grid = grid[:4500]                                     # ragged last tile
+    gen = torch.Generator().manual_seed(11)
+    off = orc.random_rotations(1, gen)[0]
+    feat = g.feat.cuda() if g.feat is not None else None
+    B = 1 if feat is None else feat.shape[0]
+    A = torch.from_numpy(g.z["fisher_A"]).cuda() if tag == "s_modelnet" else None
+    with torch.no_grad():
+        out = m.grid_log_prob(grid, feat, offset=off.cuda(), fisher_A=A, return_logp=True, g_index0=1000, mlp_mode=mode)
+        samples = grid @ off.cuda()
+        rows = None if feat is None else feat.repeat_interleave(samples.shape[0], 0)
+        Rb, ldj = m(samples.repeat(B, 1, 1), rows, mlp_mode=mode)
+    logp_ref = ldj.reshape(B, -1)
+    if A is not None:
+        A9, c = fisher_constants(A)
+        logp_ref = logp_ref + (Rb.reshape(B, -1, 9) * A9[:, None, :]).sum(-1) - c[:, None]
+    assert (out["logp"] - logp_ref).abs().max() < 2e-5
+    # the fused reduction is exactly the reduction of the log-probs the same kernel produced
+    idx, mx, lme = orc.grid_reduce(out["logp"].cpu())
+    assert torch.equal(out["argmax"].cpu(), idx + 1000)
+    assert torch.equal(out["max"].cpu(), mx)
+    lme_k = out["max"].cpu() + torch.log(out["sumexp"].cpu()) - math.log(samples.shape[0])
+    assert (lme_k - lme).abs().max() < 1e-5
+    # against the oracle (fp64) on the same inputs
+    o = orc.OracleFlow(g.cfg, g.state_dict(), torch.float64)
+    s64 = (grid.cpu().double() @ off.double())
+    lp = []
+    for b in range(B):
+        f = None if feat is None else g.feat[b:b + 1].double().expand(s64.shape[0], -1)
+        Rb64, l64 = o.forward(s64, f)
+        if A is not None:
+            l64 = l64 + orc.fisher_log_prob(A[b:b + 1].cpu().double(), Rb64)
+        lp.append(l64)
+    lp = torch.stack(lp)
+    assert rel(out["logp"].cpu().double(), lp) < 1e-4
+    oidx, omx, olme = orc.grid_reduce(lp)
+    agree = out["argmax"].cpu() - 1000 == oidx
+    # arg-max must agree unless the oracle's own top-2 are closer than fp32 noise
+    for b in range(B):
+        if not agree[b]:
+            assert abs(float(lp[b, oidx[b]] - lp[b, out["argmax"][b].item() - 1000])) < 1e-5
+    assert (lme_k.double() - olme).abs().max() < 1e-4
+
+
+def test_full_size_properties():
+    """BASELINE config 1 at full size (100 000 rotations, raw.yml): size-independent checks."""
+    g = golden("raw")
+    m = _product(g)
+    R = rgrid.generate_queries(100_000, "random")
+    with torch.no_grad():
+        Rz, ldj = m(R)
+        norm = torch.exp(ldj.double()).mean().item()       # the reference's sanity print (eval_uncondition.py:114-116)
+        Ri, li = m.inverse(Rz)
+    print(f"\n[raw full] mean exp(ldj) over 100k Haar rotations = {norm:.5f}")
+    assert abs(norm - 1.0) < 2e-2
+    assert (Rz.double() @ Rz.double().transpose(1, 2) - torch.eye(3, device="cuda", dtype=torch.float64)).abs().max() < 5e-6
+    assert (torch.linalg.det(Rz.double()) - 1).abs().max() < 5e-6
+    assert (Ri - R).abs().max().item() < 2e-4 * 24
+    assert (li + ldj).abs().max().item() < 2e-3 * 24
+    # a strided sample against the CPU oracle
+    sel = torch.arange(0, 100_000, 997)
+    o = orc.OracleFlow(g.cfg, g.state_dict(), torch.float64)
+    Ro, lo = o.forward(R[sel].cpu())
+    assert (Rz[sel].cpu().double() - Ro).abs().max() < 1e-5
+    assert rel(ldj[sel].cpu().double(), lo) < 1e-4
