@@ -1,6 +1,536 @@
-// flow_tc.cu -- tensor-core (tcgen05) conditioner path.  Placeholder until the kernel lands.
+// flow_tc.cu -- fused flow kernel with the conditioner GEMMs on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// One CTA (512 threads, one per SM, persistent) works on a PAIR of 128-rotation tiles at a time.  A tile's 128 rows are
+// the 128 TMEM lanes of its accumulator; every row is owned by two threads (column halves h = 0/1) that both keep the
+// rotation's 3x3 matrix and running log|det J| in registers across the whole layer stack (flow/flow.py:53-72).
+//
+// Per Mobius layer (flow/mobiusflow.py:46-125) and tile:
+//   CUDA cores : frame (r, v), first conditioner layer  h0 = W0[:, :3].y + b0 + c_img  (flow/condition.py:25)
+//                -> ReLU -> split into fp16 (hi, lo) -> K-major 128B-swizzled A operand in shared memory
+//   tensor core: D[128 x 64] = A . W^T as three tcgen05.mma products  Alo.Whi + Ahi.Wlo + Ahi.Whi  (fp32 accumulate in
+//                TMEM; error-compensated split => fp32-level accuracy), three times (layers.1/3/5)
+//   CUDA cores : tcgen05.ld -> + bias, ReLU (residual on the last) -> split -> A operand
+//   tensor core: fc_last  D[128 x 256] in two N=128 chunks, each committed to its own mbarrier
+//   CUDA cores : each half walks its 32 mixture components straight out of TMEM (softplus weights, Mobius maps, atan2,
+//                analytic Jacobian), the halves exchange three partial sums through shared memory.
+// Weights: the host packs, per Mobius layer, the exact shared-memory image (UMMA canonical K-major SWIZZLE_128B tiles of
+// fp16 hi / lo planes, scaled by 2^8 so that the lo plane stays in the fp16 normal range, plus the fp32 biases); one
+// cp.async.bulk (TMA bulk copy) per region brings it in, signalled on an mbarrier, and is re-issued for the next layer
+// as soon as both tiles' MMAs that read the region have completed -- so weight traffic overlaps the mixture math.
+// While one tile waits for its MMA, the other tile's 8 warps own the issue slots (ping-pong).
+//
+// Quaternion affine layers, grid mode (offset, Fisher base term, per-tile max / arg-max / sum-exp) and the row <-> image
+// mapping are identical to flow_v1.cu.
+#include <cuda_fp16.h>
+
+#include "mobius_math.cuh"
 #include "rnf_common.cuh"
+
 namespace rnf {
-bool flow_tc_supported(const rnf_flow*) { return false; }
-cudaError_t launch_flow_tc(const FlowArgs&, bool, int, cudaStream_t) { return cudaErrorNotSupported; }
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kRows = 128;                        // rows per tile = TMEM lanes
+constexpr float kWScale = 256.0f;                 // host scales the fp16 weight planes by 2^8
+constexpr float kWUnscale = 1.0f / 256.0f;
+
+// ---- shared-memory image (bytes from a 1024-aligned base); the first two regions mirror the packed global image ----
+constexpr int kHidW = 3 * 2 * 8192;               // [layer][hi|lo] 64x64 fp16, K-major SW128
+constexpr int kHidAux = 1024 + 768;               // first[64][4] fp32 ; b1,b2,b3 fp32
+constexpr int kHidBytes = kHidW + kHidAux;        // 50944
+constexpr int kLastW = 2 * 32768;                 // [hi|lo] 256x64 fp16
+constexpr int kLastBytes = kLastW + 1024;         // + permuted fc_last bias (fp32)
+constexpr int kOffHid = 0;
+constexpr int kOffLast = 51200;
+constexpr int kOffA = 117760;                     // [tile][hi|lo] 128x64 fp16 (16 KB each)
+constexpr int kOffXchg = kOffA + 4 * 16384;       // [tile][half][3][128] fp32
+constexpr int kOffRed = kOffXchg + 2 * 2 * 3 * 128 * 4;   // [tile] reduction scratch (4 warps x (float, int64) + bcast)
+constexpr int kOffBar = kOffRed + 2 * 128;
+constexpr int kOffMisc = kOffBar + 8 * 8;         // tmem base, counters, Mobius offset table
+constexpr int kSmemBytes = kOffMisc + 16 + 64 * 8;
+constexpr int kSmemAlloc = kSmemBytes + 1024;     // slack for manual 1024 B alignment
+static_assert(kHidBytes + kLastBytes == kMobFloats * 4, "TC image has the same size as the FP32 image");
+
+// mbarrier slots
+enum { BAR_HID_FULL = 0, BAR_LAST_FULL = 1, BAR_MMA = 2 /* [tile][2] -> 2..5 */ };
+
+// ------------------------------------------------ PTX wrappers ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::f16 (fp16 operands, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor layout:
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=2 (SW128) [61,64)).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=b=F16 (0), K-major both, N>>3 [17,23), M>>4 [24,29)
+__device__ __host__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Issue D[128 x N] = A[128 x 64] . W[N x 64]^T with the 3-product split.  a_* / b_* are shared addresses of the hi / lo
+// fp16 planes (each K-major SW128, 128 B per row).  Small terms are accumulated first.
+__device__ __forceinline__ void issue_split_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                                 uint32_t idesc) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, umma_desc(a_lo + 32 * k), umma_desc(b_hi + 32 * k), idesc, k > 0);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, umma_desc(a_hi + 32 * k), umma_desc(b_lo + 32 * k), idesc, 1);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, umma_desc(a_hi + 32 * k), umma_desc(b_hi + 32 * k), idesc, 1);
+}
+
+__device__ __forceinline__ float sel3(int p, float a, float b, float c) { return p == 0 ? a : (p == 1 ? b : c); }
+__device__ __forceinline__ void get_col(const float R[9], int p, float o[3]) {
+  o[0] = sel3(p, R[0], R[1], R[2]);
+  o[1] = sel3(p, R[3], R[4], R[5]);
+  o[2] = sel3(p, R[6], R[7], R[8]);
+}
+__device__ __forceinline__ void set_col(float R[9], int p, const float c[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    R[3 * i + 0] = p == 0 ? c[i] : R[3 * i + 0];
+    R[3 * i + 1] = p == 1 ? c[i] : R[3 * i + 1];
+    R[3 * i + 2] = p == 2 ? c[i] : R[3 * i + 2];
+  }
+}
+
+// Split 32 non-negative fp32 activations (columns 32h .. 32h+31 of row r) into fp16 hi / lo and store them into the
+// K-major SW128 A operand: element (r, k) lives at (r/8)*1024 + (r%8)*128 + ((k/8) ^ (r%8))*16 + (k%8)*2.
+__device__ __forceinline__ void store_a_operand(uint8_t* a_hi, uint8_t* a_lo, int r, int h, const float v[32]) {
+  const int rbase = (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x0 = v[8 * c + 2 * e], x1 = v[8 * c + 2 * e + 1];
+      const __half2 hh = __floats2half2_rn(x0, x1);
+      const float2 back = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(x0 - back.x, x1 - back.y);
+      hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    const int off = rbase + (((4 * h + c) ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+struct TileCtx {
+  int tile;        // 0 / 1 inside the CTA
+  int half;        // column half owned by this thread
+  int row;         // 0..127 = TMEM lane
+  bool elected;    // tile-local thread 0: issues MMAs and weight copies
+  uint32_t tmem_d; // TMEM address of this tile's accumulator, lane field = this warp's quarter
+  uint32_t bars;   // shared address of the mbarrier array
+  uint32_t par_mma0, par_mma1, par_hid, par_last;   // phase parities
+};
+
+template <bool GRID>
+__global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  TileCtx c;
+  c.tile = warp >> 3;
+  c.half = (warp >> 2) & 1;
+  c.row = (warp & 3) * 32 + lane;
+  c.elected = (tid & 255) == 0;
+  c.bars = smem_u32(smem + kOffBar);
+  c.par_mma0 = c.par_mma1 = c.par_hid = c.par_last = 0;
+
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kOffMisc);
+  int* s_cnt = reinterpret_cast<int*>(smem + kOffMisc + 4);            // [0] hid, [1] last
+  long long* s_moff = reinterpret_cast<long long*>(smem + kOffMisc + 16);  // w_off_tc of Mobius layers, execution order
+
+  // ---- one-time setup -------------------------------------------------------------------------------------------------
+  int n_mob = 0;
+  for (int i = 0; i < a.n_layers; ++i)
+    if (a.layers[i].kind == RNF_LAYER_MOBIUS) {
+      if (tid == 0) s_moff[n_mob] = a.layers[i].w_off_tc;
+      ++n_mob;
+    }
+  if (tid == 0) {
+    mbar_init(c.bars + 8 * BAR_HID_FULL, 1);
+    mbar_init(c.bars + 8 * BAR_LAST_FULL, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(c.bars + 8 * (BAR_MMA + i), 1);
+    s_cnt[0] = s_cnt[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  c.tmem_d = tmem_base + (uint32_t)(c.tile * 256) + ((uint32_t)((warp & 3) * 32) << 16);
+
+  const int64_t n_pairs = (a.n_tiles + 1) / 2;
+  const int64_t my_items = blockIdx.x < n_pairs ? (n_pairs - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const int64_t total_steps = my_items * n_mob;     // Mobius layer executions of this CTA
+  const uint8_t* wbytes = reinterpret_cast<const uint8_t*>(a.weights);
+  if (tid == 0 && total_steps > 0) {                // prime both weight regions with the first Mobius layer
+    const uint8_t* src = wbytes + s_moff[0] * 4;
+    mbar_expect_tx(c.bars + 8 * BAR_HID_FULL, kHidBytes);
+    bulk_g2s(smem_u32(smem + kOffHid), src, kHidBytes, c.bars + 8 * BAR_HID_FULL);
+    mbar_expect_tx(c.bars + 8 * BAR_LAST_FULL, kLastBytes);
+    bulk_g2s(smem_u32(smem + kOffLast), src + kHidBytes, kLastBytes, c.bars + 8 * BAR_LAST_FULL);
+  }
+
+  uint8_t* a_hi = smem + kOffA + c.tile * 32768;
+  uint8_t* a_lo = a_hi + 16384;
+  const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo);
+  const uint32_t w_hid_s = smem_u32(smem + kOffHid), w_last_s = smem_u32(smem + kOffLast);
+  const float4* sFirst = reinterpret_cast<const float4*>(smem + kOffHid + kHidW);
+  const float* sBiasHid = reinterpret_cast<const float*>(smem + kOffHid + kHidW + 1024);
+  const float* sBiasLast = reinterpret_cast<const float*>(smem + kOffLast + kLastW);
+  float* xchg = reinterpret_cast<float*>(smem + kOffXchg) + c.tile * (2 * 3 * 128);
+  const int bar_tile = 1 + c.tile;                   // named barrier of the tile's 256 threads
+  const uint32_t bar_mma0 = c.bars + 8 * (BAR_MMA + 2 * c.tile), bar_mma1 = bar_mma0 + 8;
+  int64_t step = 0;                                  // Mobius executions finished by this tile (same on both tiles)
+
+  for (int64_t item = 0; item < my_items; ++item) {
+    const int64_t tile_idx = 2 * (blockIdx.x + item * (int64_t)gridDim.x) + c.tile;
+    int64_t row = 0, img = 0, g = 0;
+    bool valid = false;
+    float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+    if (tile_idx < a.n_tiles) {
+      if (GRID) {
+        img = tile_idx / a.tiles_per_image;
+        g = (tile_idx % a.tiles_per_image) * kRows + c.row;
+        valid = g < a.G;
+        row = img * a.G + g;
+        if (valid) {
+          float Gm[9];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) Gm[i] = __ldg(a.R_in + g * 9 + i);
+          if (a.offset != nullptr) {                 // samples = grid @ random_rot (eval.py:439-440)
+            float O[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) O[i] = __ldg(a.offset + i);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+                R[3 * i + j] = fmaf(Gm[3 * i + 2], O[6 + j], fmaf(Gm[3 * i + 1], O[3 + j], Gm[3 * i] * O[j]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) R[i] = Gm[i];
+          }
+        }
+      } else {
+        row = tile_idx * kRows + c.row;
+        valid = row < a.N;
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) R[i] = __ldg(a.R_in + row * 9 + i);
+          if (a.cond != nullptr) img = a.feat_index != nullptr ? (int64_t)__ldg(a.feat_index + row) : row / a.rows_per_image;
+        }
+      }
+    }
+    const float* cond_img = a.cond != nullptr ? a.cond + img * a.cond_stride : nullptr;
+    float ldj = 0.0f;
+
+#pragma unroll 1
+    for (int li = 0; li < a.n_layers; ++li) {
+      const LayerDev L = a.layers[li];
+      if (L.kind != RNF_LAYER_MOBIUS) {
+        const float* W = L.cond_slot >= 0 ? cond_img + (int64_t)a.n_mobius_slots * kH + (int64_t)L.cond_slot * kAffFloats
+                                          : a.weights + L.w_off;
+        float Wr[17];
+#pragma unroll
+        for (int i = 0; i < 17; ++i) Wr[i] = __ldg(W + i);
+        const float loglen = quat_affine(Wr, R);
+        if (L.has_ldj) ldj += Wr[16] - 4.0f * loglen;
+        continue;
+      }
+      // ================================ Mobius layer ================================
+      const int p0 = L.perm, p1 = (L.perm + 1) % 3, p2 = (L.perm + 2) % 3;
+      float x[3], y[3], r[3], v[3];
+      get_col(R, p0, x);
+      get_col(R, p1, y);
+      make_frame(x, y, r, v);
+      const float* cimg = (L.cond_slot >= 0 && cond_img != nullptr) ? cond_img + (int64_t)L.cond_slot * kH : nullptr;
+
+      // the aux block (first layer, biases) arrives with the hidden weights: every thread observes the copy itself
+      mbar_wait(c.bars + 8 * BAR_HID_FULL, c.par_hid);
+      c.par_hid ^= 1;
+
+      // ---- first conditioner layer for my 32 columns, kept for the residual ----
+      float h0[32];
+      {
+        float act[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float4 f = sFirst[32 * c.half + j];
+          float hv = fmaf(f.z, y[2], fmaf(f.y, y[1], fmaf(f.x, y[0], f.w)));
+          if (cimg != nullptr) hv += __ldg(cimg + 32 * c.half + j);
+          h0[j] = hv;
+          act[j] = fmaxf(hv, 0.0f);
+        }
+        store_a_operand(a_hi, a_lo, c.row, c.half, act);
+      }
+      // ---- three hidden layers on the tensor core ----
+#pragma unroll 1
+      for (int l = 0; l < 3; ++l) {
+        fence_proxy_async();
+        tc_fence_before();
+        named_bar(bar_tile, 256);
+        if (c.elected) {
+          tc_fence_after();
+          const uint32_t wb = w_hid_s + l * 16384;
+          issue_split_gemm(tmem_base + c.tile * 256, a_hi_s, a_lo_s, wb, wb + 8192, umma_idesc(128, 64));
+          umma_commit(bar_mma0);
+        }
+        mbar_wait(bar_mma0, c.par_mma0);
+        c.par_mma0 ^= 1;
+        tc_fence_after();
+        float acc[32];
+        tmem_ld32(c.tmem_d + 32 * c.half, acc);
+        const float* bias = sBiasHid + 64 * l + 32 * c.half;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = fmaf(acc[j], kWUnscale, bias[j]);
+          if (l == 2) t += h0[j];                    // relu_last(x0 + x)   (flow/condition.py:29)
+          acc[j] = fmaxf(t, 0.0f);
+        }
+        store_a_operand(a_hi, a_lo, c.row, c.half, acc);
+      }
+      // ---- fc_last: two N = 128 chunks, own barrier each ----
+      fence_proxy_async();
+      tc_fence_before();
+      named_bar(bar_tile, 256);
+      mbar_wait(c.bars + 8 * BAR_LAST_FULL, c.par_last);   // weights for the MMA, permuted bias for every thread
+      c.par_last ^= 1;
+      if (c.elected) {
+        // The hidden region (weights + biases) is free once every thread of BOTH tiles is past the third hidden
+        // epilogue (the barrier above) : the second tile to get here refills it for the next Mobius layer.
+        const int old = atomicAdd(&s_cnt[0], 1);
+        if ((old & 1) && step + 1 < total_steps) {
+          const uint8_t* src = wbytes + s_moff[(step + 1) % n_mob] * 4;
+          mbar_expect_tx(c.bars + 8 * BAR_HID_FULL, kHidBytes);
+          bulk_g2s(smem_u32(smem + kOffHid), src, kHidBytes, c.bars + 8 * BAR_HID_FULL);
+        }
+        tc_fence_after();
+        const uint32_t d = tmem_base + c.tile * 256;
+        issue_split_gemm(d, a_hi_s, a_lo_s, w_last_s, w_last_s + 32768, umma_idesc(128, 128));
+        umma_commit(bar_mma0);
+        issue_split_gemm(d + 128, a_hi_s, a_lo_s, w_last_s + 16384, w_last_s + 32768 + 16384, umma_idesc(128, 128));
+        umma_commit(bar_mma1);
+      }
+      if (c.half == 0) { mbar_wait(bar_mma0, c.par_mma0); } else { mbar_wait(bar_mma1, c.par_mma1); }
+      c.par_mma0 ^= 1;                               // both barriers complete exactly once per layer here
+      c.par_mma1 ^= 1;
+      tc_fence_after();
+
+      // ---- mixture of 32 components (my half), 8 at a time straight from TMEM ----
+      float S_sp = 0.0f, S_th = 0.0f, S_f = 0.0f;
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        float acc[32];
+        tmem_ld32(c.tmem_d + 128 * c.half + 32 * q, acc);
+        const float4* b4 = reinterpret_cast<const float4*>(sBiasLast + 128 * c.half + 32 * q);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float4 b = b4[k];
+          const float sp = softplus_torch(fmaf(acc[4 * k], kWUnscale, b.x));
+          float w[3] = {fmaf(acc[4 * k + 1], kWUnscale, b.y), fmaf(acc[4 * k + 2], kWUnscale, b.z),
+                        fmaf(acc[4 * k + 3], kWUnscale, b.w)};
+          comp_prep(w, y);
+          float th, f;
+          comp_eval(x, w, r, v, th, f);
+          S_sp += sp;
+          S_th = fmaf(sp, th, S_th);
+          S_f = fmaf(sp, f, S_f);
+        }
+      }
+      // ---- exchange partial sums between the two halves of the row (fixed summation order) ----
+      float* mine = xchg + c.half * 384 + c.row;
+      mine[0] = S_sp; mine[128] = S_th; mine[256] = S_f;
+      tc_fence_before();
+      named_bar(bar_tile, 256);
+      // Past this barrier every thread of the tile is done with the fc_last bias and both MMA chunks have completed
+      // (half 1 waited for chunk B): the second tile to get here refills the fc_last region.
+      if (c.elected) {
+        const int old = atomicAdd(&s_cnt[1], 1);
+        if ((old & 1) && step + 1 < total_steps) {
+          const uint8_t* src = wbytes + s_moff[(step + 1) % n_mob] * 4 + kHidBytes;
+          mbar_expect_tx(c.bars + 8 * BAR_LAST_FULL, kLastBytes);
+          bulk_g2s(smem_u32(smem + kOffLast), src, kLastBytes, c.bars + 8 * BAR_LAST_FULL);
+        }
+      }
+      {
+        const float* lo_half = xchg + c.row;
+        const float* hi_half = xchg + 384 + c.row;
+        S_sp = lo_half[0] + hi_half[0];
+        S_th = lo_half[128] + hi_half[128];
+        S_f = lo_half[256] + hi_half[256];
+      }
+      float nx[3], nz[3];
+      circle_point(r, v, S_th / S_sp, nx);
+      ldj += logf(S_f / S_sp);
+      cross3(nx, y, nz);
+      normalize3(nz);
+      set_col(R, p0, nx);
+      set_col(R, p2, nz);
+      ++step;
+    }
+
+    // ================================ outputs ================================
+    if (!GRID) {
+      if (valid && c.half == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) a.R_out[row * 9 + i] = R[i];
+        a.ldj_out[row] = ldj;
+      }
+    } else if (tile_idx < a.n_tiles) {
+      // both halves run the reduction code path only on half 0 (4 warps = 128 rows); barrier id 3 + tile
+      if (c.half == 0) {
+        float lp = ldj;
+        if (a.fisher_A != nullptr) {
+          float tr = 0.0f;
+#pragma unroll
+          for (int i = 0; i < 9; ++i) tr = fmaf(__ldg(a.fisher_A + img * 9 + i), R[i], tr);
+          lp += tr - __ldg(a.fisher_c + img);
+        }
+        if (!valid) lp = -INFINITY;
+        if (a.logp_out != nullptr && valid) a.logp_out[row] = lp;
+        float* s_v = reinterpret_cast<float*>(smem + kOffRed + c.tile * 128);            // [4] + bcast at [4]
+        long long* s_i = reinterpret_cast<long long*>(smem + kOffRed + c.tile * 128 + 32);  // [4] + bcast at [4]
+        const int w4 = warp & 3;
+        float bv = lp;
+        long long bi = valid ? (long long)g : 0x7fffffffffffffffLL;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_v[w4] = bv; s_i[w4] = bi; }
+        named_bar(3 + c.tile, 128);
+        bv = s_v[0]; bi = s_i[0];
+#pragma unroll
+        for (int w = 1; w < 4; ++w) {
+          const float ov = s_v[w];
+          const long long oi = s_i[w];
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        const float m = bv;
+        float e = (valid && m > -INFINITY) ? expf(lp - m) : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        named_bar(3 + c.tile, 128);                  // everybody has read s_v / s_i
+        if (lane == 0) s_v[w4] = e;
+        named_bar(3 + c.tile, 128);
+        if (c.row == 0) {
+          const float s = (s_v[0] + s_v[1]) + (s_v[2] + s_v[3]);
+          float* p = a.part + tile_idx * 4;
+          p[0] = m;
+          p[1] = s;
+          p[2] = __int_as_float((int)(bi & 0xffffffffLL));
+          p[3] = __int_as_float((int)(bi >> 32));
+        }
+        named_bar(3 + c.tile, 128);                  // scratch reusable by the next item
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+}  // namespace
+
+bool flow_tc_supported(const rnf_flow* f) {
+  for (int i = 0; i < f->model.n_layers; ++i)
+    if (f->layers_host[i].kind == RNF_LAYER_MOBIUS && f->layers_host[i].w_off_tc < 0) return false;
+  return true;
+}
+
+cudaError_t launch_flow_tc(const FlowArgs& a, bool inverse, int sm_count, cudaStream_t st) {
+  if (inverse) return cudaErrorNotSupported;
+  const bool grid_mode = a.G > 0;
+  void (*kern)(const FlowArgs) = grid_mode ? flow_tc_kernel<true> : flow_tc_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc);
+  if (e != cudaSuccess) return e;
+  if (a.n_tiles <= 0) return cudaSuccess;
+  const int64_t pairs = (a.n_tiles + 1) / 2;
+  const int64_t grid = pairs < sm_count ? pairs : sm_count;
+  kern<<<(unsigned)grid, kThreads, kSmemAlloc, st>>>(a);
+  return cudaGetLastError();
+}
+
 }  // namespace rnf

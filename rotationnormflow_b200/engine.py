@@ -23,7 +23,8 @@ AFF_FLOATS = 40
 AFF_INV = 20
 CAFF_FLOATS = 64 + 3 * (64 * 64 + 64) + 16 * 64 + 16
 
-TC_AVAILABLE = False   # set once csrc/flow_tc.cu carries the tcgen05 conditioner
+TC_AVAILABLE = True    # csrc/flow_tc.cu: tcgen05 conditioner (forward / grid); the inverse still runs the FP32 kernel
+TC_WEIGHT_SCALE = 256.0  # fp16 weight planes are stored times 2^8 (kWScale in csrc/flow_tc.cu)
 
 _MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC}
 
@@ -68,6 +69,47 @@ def pack_mobius(cond_sd: dict, F: int) -> tuple[np.ndarray, np.ndarray | None]:
     blk[o:o + 256] = b4[perm]; o += 256
     assert o == MOB_FLOATS
     return blk, (np.ascontiguousarray(W0[:, 3:]) if F > 0 else None)
+
+
+def _umma_k_major_sw128(W: np.ndarray) -> np.ndarray:
+    """[N,64] fp16 -> bytes of the UMMA canonical K-major SWIZZLE_128B tile (N multiple of 8): element (n,k) at
+    (n/8)*1024 + (n%8)*128 + ((k/8) ^ (n%8))*16 + (k%8)*2   (cute::UMMA::Layout_K_SW128_Atom)."""
+    N, K = W.shape
+    assert K == 64 and N % 8 == 0 and W.dtype == np.float16
+    n = np.arange(N)[:, None]
+    k = np.arange(K)[None, :]
+    off = (n // 8) * 1024 + (n % 8) * 128 + (((k // 8) ^ (n % 8)) * 16) + (k % 8) * 2      # byte offsets
+    out = np.zeros(N * 64, dtype=np.float16)
+    out[(off // 2).reshape(-1)] = W.reshape(-1)
+    return out
+
+
+def _split_fp16(W: np.ndarray):
+    Ws = W.astype(np.float32) * np.float32(TC_WEIGHT_SCALE)
+    hi = Ws.astype(np.float16)
+    lo = (Ws - hi.astype(np.float32)).astype(np.float16)
+    return hi, lo
+
+
+def pack_mobius_tc(cond_sd: dict) -> np.ndarray:
+    """Tensor-core image of one Mobius conditioner = the exact shared-memory image of csrc/flow_tc.cu:
+    [3 x (hi 64x64, lo 64x64) fp16 SW128 | first[64][4] fp32 | b1,b2,b3 fp32 | (hi 256x64, lo 256x64) fp16 SW128 | b4' fp32]
+    returned as float32 words (MOB_FLOATS of them)."""
+    W0, b0 = _np(cond_sd["fc_first.weight"]), _np(cond_sd["fc_first.bias"])
+    parts = []
+    for j in (1, 3, 5):
+        hi, lo = _split_fp16(_np(cond_sd[f"layers.{j}.weight"]))          # nn.Linear weight is [out=N, in=K]: K-major
+        parts += [_umma_k_major_sw128(hi).view(np.float32), _umma_k_major_sw128(lo).view(np.float32)]
+    parts.append(np.concatenate([W0[:, :3], b0[:, None]], axis=1).astype(np.float32).reshape(-1))
+    for j in (1, 3, 5):
+        parts.append(_np(cond_sd[f"layers.{j}.bias"]))
+    perm = _last_layer_perm(K_SEGMENTS)
+    hi, lo = _split_fp16(_np(cond_sd["fc_last.weight"])[perm])
+    parts += [_umma_k_major_sw128(hi).view(np.float32), _umma_k_major_sw128(lo).view(np.float32)]
+    parts.append(_np(cond_sd["fc_last.bias"])[perm])
+    blk = np.concatenate(parts).astype(np.float32, copy=False)
+    assert blk.size == MOB_FLOATS
+    return blk
 
 
 def pack_affine_matrix(W: torch.Tensor, is_rot: bool) -> np.ndarray:
@@ -154,8 +196,10 @@ class Program:
             d.w_off_tc = -1
             if s.kind == "mobius":
                 d.kind = _cabi.RNF_LAYER_MOBIUS
-                blk, wf = pack_mobius(_sub_sd(s.module, "conditioner."), self.F if s.module.condition else 0)
+                csd = _sub_sd(s.module, "conditioner.")
+                blk, wf = pack_mobius(csd, self.F if s.module.condition else 0)
                 d.w_off = push(blk)
+                d.w_off_tc = push(pack_mobius_tc(csd))
                 if wf is not None:
                     d.cond_slot = n_mob
                     n_mob += 1
@@ -246,6 +290,7 @@ class Program:
         m = _MODES[mode]
         with torch.cuda.device(self.device):
             if inverse:
+                m = _cabi.RNF_MLP_FP32          # the bisection path exists in the FP32 kernel only (this revision)
                 ns = int(self.lib.rnf_flow_inverse_scratch_floats(self.handle, N))
                 scratch = torch.empty((max(ns, 1),), device=self.device, dtype=torch.float32)
                 _cabi.check(self.lib.rnf_flow_inverse(self.handle, C.c_void_p(R.data_ptr()), N, cp, B, ip, rows_per_image,
