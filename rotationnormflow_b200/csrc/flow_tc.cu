@@ -23,7 +23,7 @@
 // mapping are identical to flow_v1.cu.
 #include <cuda_fp16.h>
 
-#include "mobius_math.cuh"
+#include "mobius_fast.cuh"
 #include "rnf_common.cuh"
 
 namespace rnf {
@@ -31,7 +31,6 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kRows = 128;                        // rows per tile = TMEM lanes
-constexpr float kWScale = 256.0f;                 // host scales the fp16 weight planes by 2^8
 constexpr float kWUnscale = 1.0f / 256.0f;
 
 // ---- shared-memory image (bytes from a 1024-aligned base); the first two regions mirror the packed global image ----
@@ -121,6 +120,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// the inverse: 32 registers -> 32 consecutive fp32 columns of the thread's own TMEM lane (private scratch)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float v[32]) {
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]),
+      "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]), "r"(u[16]), "r"(u[17]), "r"(u[18]),
+      "r"(u[19]), "r"(u[20]), "r"(u[21]), "r"(u[22]), "r"(u[23]), "r"(u[24]), "r"(u[25]), "r"(u[26]), "r"(u[27]),
+      "r"(u[28]), "r"(u[29]), "r"(u[30]), "r"(u[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor layout:
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=2 (SW128) [61,64)).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -190,10 +204,11 @@ struct TileCtx {
   uint32_t par_mma0, par_mma1, par_hid, par_last;   // phase parities
 };
 
-template <bool GRID>
+template <bool INV, bool GRID>
 __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // manual 1024 B alignment (SWIZZLE_128B atoms) done on the shared-window address so the pointer stays a shared pointer
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
 
@@ -206,16 +221,18 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
   c.par_mma0 = c.par_mma1 = c.par_hid = c.par_last = 0;
 
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kOffMisc);
-  int* s_cnt = reinterpret_cast<int*>(smem + kOffMisc + 4);            // [0] hid, [1] last
+  int* s_cnt = reinterpret_cast<int*>(smem + kOffMisc + 4);                // [0] hid, [1] last
   long long* s_moff = reinterpret_cast<long long*>(smem + kOffMisc + 16);  // w_off_tc of Mobius layers, execution order
 
   // ---- one-time setup -------------------------------------------------------------------------------------------------
   int n_mob = 0;
-  for (int i = 0; i < a.n_layers; ++i)
-    if (a.layers[i].kind == RNF_LAYER_MOBIUS) {
-      if (tid == 0) s_moff[n_mob] = a.layers[i].w_off_tc;
+  for (int i = 0; i < a.n_layers; ++i) {
+    const int li = INV ? a.n_layers - 1 - i : i;
+    if (a.layers[li].kind == RNF_LAYER_MOBIUS) {
+      if (tid == 0) s_moff[n_mob] = a.layers[li].w_off_tc;
       ++n_mob;
     }
+  }
   if (tid == 0) {
     mbar_init(c.bars + 8 * BAR_HID_FULL, 1);
     mbar_init(c.bars + 8 * BAR_LAST_FULL, 1);
@@ -252,9 +269,14 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
   const float4* sFirst = reinterpret_cast<const float4*>(smem + kOffHid + kHidW);
   const float* sBiasHid = reinterpret_cast<const float*>(smem + kOffHid + kHidW + 1024);
   const float* sBiasLast = reinterpret_cast<const float*>(smem + kOffLast + kLastW);
-  float* xchg = reinterpret_cast<float*>(smem + kOffXchg) + c.tile * (2 * 3 * 128);
+  float* xchg = reinterpret_cast<float*>(smem + kOffXchg) + c.tile * (2 * 3 * 128);   // [half][slot 0..2][row]
+  float* x_mine = xchg + c.half * 384 + c.row;
+  const float* x_lo = xchg + c.row;
+  const float* x_hi = xchg + 384 + c.row;
   const int bar_tile = 1 + c.tile;                   // named barrier of the tile's 256 threads
   const uint32_t bar_mma0 = c.bars + 8 * (BAR_MMA + 2 * c.tile), bar_mma1 = bar_mma0 + 8;
+  const uint32_t tm_stash = c.tmem_d + 64 + 32 * c.half;     // h0 of my 32 hidden columns (free TMEM columns)
+  const uint32_t tm_mine = c.tmem_d + 128 * c.half;          // my 128 fc_last columns = 32 mixture components
   int64_t step = 0;                                  // Mobius executions finished by this tile (same on both tiles)
 
   for (int64_t item = 0; item < my_items; ++item) {
@@ -300,11 +322,13 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
     float ldj = 0.0f;
 
 #pragma unroll 1
-    for (int li = 0; li < a.n_layers; ++li) {
+    for (int lstep = 0; lstep < a.n_layers; ++lstep) {
+      const int li = INV ? a.n_layers - 1 - lstep : lstep;
       const LayerDev L = a.layers[li];
       if (L.kind != RNF_LAYER_MOBIUS) {
         const float* W = L.cond_slot >= 0 ? cond_img + (int64_t)a.n_mobius_slots * kH + (int64_t)L.cond_slot * kAffFloats
                                           : a.weights + L.w_off;
+        if (INV) W += kAffInv;
         float Wr[17];
 #pragma unroll
         for (int i = 0; i < 17; ++i) Wr[i] = __ldg(W + i);
@@ -314,29 +338,35 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       }
       // ================================ Mobius layer ================================
       const int p0 = L.perm, p1 = (L.perm + 1) % 3, p2 = (L.perm + 2) % 3;
-      float x[3], y[3], r[3], v[3];
+      float x[3], y[3];
+      Plane P;
       get_col(R, p0, x);
       get_col(R, p1, y);
-      make_frame(x, y, r, v);
+      make_frame(x, y, P.r, P.v);
       const float* cimg = (L.cond_slot >= 0 && cond_img != nullptr) ? cond_img + (int64_t)L.cond_slot * kH : nullptr;
 
       // the aux block (first layer, biases) arrives with the hidden weights: every thread observes the copy itself
       mbar_wait(c.bars + 8 * BAR_HID_FULL, c.par_hid);
       c.par_hid ^= 1;
 
-      // ---- first conditioner layer for my 32 columns, kept for the residual ----
-      float h0[32];
+      // ---- first conditioner layer for my 32 columns; pre-activation stashed in TMEM for the residual ----
       {
-        float act[32];
+        float h0[32], act[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float4 f = sFirst[32 * c.half + j];
-          float hv = fmaf(f.z, y[2], fmaf(f.y, y[1], fmaf(f.x, y[0], f.w)));
-          if (cimg != nullptr) hv += __ldg(cimg + 32 * c.half + j);
-          h0[j] = hv;
-          act[j] = fmaxf(hv, 0.0f);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cimg != nullptr) cf = __ldg(reinterpret_cast<const float4*>(cimg + 32 * c.half) + j4);
+          const float cc[4] = {cf.x, cf.y, cf.z, cf.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float4 f = sFirst[32 * c.half + 4 * j4 + e];
+            const float hv = fmaf(f.z, y[2], fmaf(f.y, y[1], fmaf(f.x, y[0], f.w))) + cc[e];
+            h0[4 * j4 + e] = hv;
+            act[4 * j4 + e] = fmaxf(hv, 0.0f);
+          }
         }
         store_a_operand(a_hi, a_lo, c.row, c.half, act);
+        tmem_st32(tm_stash, h0);
       }
       // ---- three hidden layers on the tensor core ----
 #pragma unroll 1
@@ -355,12 +385,27 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
         tc_fence_after();
         float acc[32];
         tmem_ld32(c.tmem_d + 32 * c.half, acc);
-        const float* bias = sBiasHid + 64 * l + 32 * c.half;
+        const float4* bias4 = reinterpret_cast<const float4*>(sBiasHid + 64 * l + 32 * c.half);
+        if (l < 2) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = fmaf(acc[j], kWUnscale, bias[j]);
-          if (l == 2) t += h0[j];                    // relu_last(x0 + x)   (flow/condition.py:29)
-          acc[j] = fmaxf(t, 0.0f);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = bias4[j4];
+            acc[4 * j4 + 0] = fmaxf(fmaf(acc[4 * j4 + 0], kWUnscale, b.x), 0.0f);
+            acc[4 * j4 + 1] = fmaxf(fmaf(acc[4 * j4 + 1], kWUnscale, b.y), 0.0f);
+            acc[4 * j4 + 2] = fmaxf(fmaf(acc[4 * j4 + 2], kWUnscale, b.z), 0.0f);
+            acc[4 * j4 + 3] = fmaxf(fmaf(acc[4 * j4 + 3], kWUnscale, b.w), 0.0f);
+          }
+        } else {                                     // relu_last(x0 + x)   (flow/condition.py:29)
+          float h0[32];
+          tmem_ld32(tm_stash, h0);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = bias4[j4];
+            acc[4 * j4 + 0] = fmaxf(fmaf(acc[4 * j4 + 0], kWUnscale, b.x) + h0[4 * j4 + 0], 0.0f);
+            acc[4 * j4 + 1] = fmaxf(fmaf(acc[4 * j4 + 1], kWUnscale, b.y) + h0[4 * j4 + 1], 0.0f);
+            acc[4 * j4 + 2] = fmaxf(fmaf(acc[4 * j4 + 2], kWUnscale, b.z) + h0[4 * j4 + 2], 0.0f);
+            acc[4 * j4 + 3] = fmaxf(fmaf(acc[4 * j4 + 3], kWUnscale, b.w) + h0[4 * j4 + 3], 0.0f);
+          }
         }
         store_a_operand(a_hi, a_lo, c.row, c.half, acc);
       }
@@ -372,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       c.par_last ^= 1;
       if (c.elected) {
         // The hidden region (weights + biases) is free once every thread of BOTH tiles is past the third hidden
-        // epilogue (the barrier above) : the second tile to get here refills it for the next Mobius layer.
+        // epilogue (the barrier above): the second tile to get here refills it for the next Mobius layer.
         const int old = atomicAdd(&s_cnt[0], 1);
         if ((old & 1) && step + 1 < total_steps) {
           const uint8_t* src = wbytes + s_moff[(step + 1) % n_mob] * 4;
@@ -391,30 +436,35 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       c.par_mma1 ^= 1;
       tc_fence_after();
 
-      // ---- mixture of 32 components (my half), 8 at a time straight from TMEM ----
+      // ---- mixture of my 32 components, 8 at a time straight from TMEM ----
       float S_sp = 0.0f, S_th = 0.0f, S_f = 0.0f;
+      const float zr = dot3(x, P.r), zv = dot3(x, P.v);   // in-plane coordinates of the moving column
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         float acc[32];
-        tmem_ld32(c.tmem_d + 128 * c.half + 32 * q, acc);
+        tmem_ld32(tm_mine + 32 * q, acc);
         const float4* b4 = reinterpret_cast<const float4*>(sBiasLast + 128 * c.half + 32 * q);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float4 b = b4[k];
-          const float sp = softplus_torch(fmaf(acc[4 * k], kWUnscale, b.x));
-          float w[3] = {fmaf(acc[4 * k + 1], kWUnscale, b.y), fmaf(acc[4 * k + 2], kWUnscale, b.z),
-                        fmaf(acc[4 * k + 3], kWUnscale, b.w)};
-          comp_prep(w, y);
-          float th, f;
-          comp_eval(x, w, r, v, th, f);
+          const float sp = softplus_fast(fmaf(acc[4 * k], kWUnscale, b.x));
+          float al, be, omw;
+          comp_prep2(P, fmaf(acc[4 * k + 1], kWUnscale, b.y), fmaf(acc[4 * k + 2], kWUnscale, b.z),
+                     fmaf(acc[4 * k + 3], kWUnscale, b.w), al, be, omw);
           S_sp += sp;
-          S_th = fmaf(sp, th, S_th);
-          S_f = fmaf(sp, f, S_f);
+          if (!INV) {
+            float th, f;
+            comp_eval2(zr, zv, al, be, omw, th, f);
+            S_th = fmaf(sp, th, S_th);
+            S_f = fmaf(sp, f, S_f);
+          } else {
+            acc[4 * k] = al; acc[4 * k + 1] = be; acc[4 * k + 2] = omw; acc[4 * k + 3] = sp;
+          }
         }
+        if (INV) tmem_st32(tm_mine + 32 * q, acc);   // prepared parameters stay in my TMEM lane for the bisection
       }
       // ---- exchange partial sums between the two halves of the row (fixed summation order) ----
-      float* mine = xchg + c.half * 384 + c.row;
-      mine[0] = S_sp; mine[128] = S_th; mine[256] = S_f;
+      x_mine[0] = S_sp; x_mine[128] = S_th; x_mine[256] = S_f;
       tc_fence_before();
       named_bar(bar_tile, 256);
       // Past this barrier every thread of the tile is done with the fc_last bias and both MMA chunks have completed
@@ -427,16 +477,64 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
           bulk_g2s(smem_u32(smem + kOffLast), src, kLastBytes, c.bars + 8 * BAR_LAST_FULL);
         }
       }
-      {
-        const float* lo_half = xchg + c.row;
-        const float* hi_half = xchg + 384 + c.row;
-        S_sp = lo_half[0] + hi_half[0];
-        S_th = lo_half[128] + hi_half[128];
-        S_f = lo_half[256] + hi_half[256];
-      }
+      S_sp = x_lo[0] + x_hi[0];
       float nx[3], nz[3];
-      circle_point(r, v, S_th / S_sp, nx);
-      ldj += logf(S_f / S_sp);
+      if (!INV) {
+        S_th = x_lo[128] + x_hi[128];
+        S_f = x_lo[256] + x_hi[256];
+        circle_point(P.r, P.v, S_th / S_sp, nx);
+        ldj += logf(S_f / S_sp);
+      } else {
+        // target angle of the given column in its own frame (flow/mobiusflow.py:157-167); ~pi by construction
+        float ys = atan2f(zv, zr);
+        ys = ys >= 0.0f ? ys : ys + kTwoPi;
+        if (fabsf(ys - kTwoPi) < 1e-4f) ys = 0.0f;
+        // BinFind.forward (flow/mobiusflow.py:196-224): bracket [pi/2, 3pi/2], 15 halvings, return the last probe.
+        // Each half sums its 32 components; partial sums ping-pong through two exchange slots (one barrier per probe).
+        float lo = kPi / 2.0f, hi = 1.5f * kPi, x0 = 0.0f;
+#pragma unroll 1
+        for (int it = 0; it < 15; ++it) {
+          x0 = (lo + hi) / 2.0f;
+          float sn, cs;
+          sincosf(x0, &sn, &cs);
+          float Fs = 0.0f;
+#pragma unroll 1
+          for (int q = 0; q < 4; ++q) {
+            float prm[32];
+            tmem_ld32(tm_mine + 32 * q, prm);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              float th, f;
+              comp_eval2(cs, sn, prm[4 * k], prm[4 * k + 1], prm[4 * k + 2], th, f);
+              Fs = fmaf(prm[4 * k + 3], th, Fs);
+            }
+          }
+          const int slot = (1 + (it & 1)) * 128;     // slots 1 / 2 (slot 0 still holds S_sp of slow readers)
+          x_mine[slot] = Fs;
+          named_bar(bar_tile, 256);
+          const float fx0 = (x_lo[slot] + x_hi[slot]) / S_sp - ys;
+          const float half_w = (hi - lo) / 2.0f;
+          if (fx0 < 0.0f) lo = lo + half_w;
+          else if (fx0 >= 0.0f) hi = hi - half_w;
+        }
+        float sn, cs;
+        sincosf(x0, &sn, &cs);
+        nx[0] = fmaf(P.v[0], sn, P.r[0] * cs);
+        nx[1] = fmaf(P.v[1], sn, P.r[1] * cs);
+        nx[2] = fmaf(P.v[2], sn, P.r[2] * cs);
+        float Sf = 0.0f;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          float prm[32];
+          tmem_ld32(tm_mine + 32 * q, prm);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) Sf = fmaf(prm[4 * k + 3], comp_f2(cs, sn, prm[4 * k], prm[4 * k + 1], prm[4 * k + 2]), Sf);
+        }
+        x_mine[0] = Sf;                              // slot 0: everybody read S_sp before the first probe barrier
+        tc_fence_before();
+        named_bar(bar_tile, 256);
+        ldj -= logf((x_lo[0] + x_hi[0]) / S_sp);
+      }
       cross3(nx, y, nz);
       normalize3(nz);
       set_col(R, p0, nx);
@@ -452,7 +550,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
         a.ldj_out[row] = ldj;
       }
     } else if (tile_idx < a.n_tiles) {
-      // both halves run the reduction code path only on half 0 (4 warps = 128 rows); barrier id 3 + tile
+      // the per-tile reduction runs on half 0 (4 warps = 128 rows); named barrier id 3 + tile
       if (c.half == 0) {
         float lp = ldj;
         if (a.fisher_A != nullptr) {
@@ -463,8 +561,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
         }
         if (!valid) lp = -INFINITY;
         if (a.logp_out != nullptr && valid) a.logp_out[row] = lp;
-        float* s_v = reinterpret_cast<float*>(smem + kOffRed + c.tile * 128);            // [4] + bcast at [4]
-        long long* s_i = reinterpret_cast<long long*>(smem + kOffRed + c.tile * 128 + 32);  // [4] + bcast at [4]
+        float* s_v = reinterpret_cast<float*>(smem + kOffRed + c.tile * 128);
+        long long* s_i = reinterpret_cast<long long*>(smem + kOffRed + c.tile * 128 + 32);
         const int w4 = warp & 3;
         float bv = lp;
         long long bi = valid ? (long long)g : 0x7fffffffffffffffLL;
@@ -521,9 +619,9 @@ bool flow_tc_supported(const rnf_flow* f) {
 }
 
 cudaError_t launch_flow_tc(const FlowArgs& a, bool inverse, int sm_count, cudaStream_t st) {
-  if (inverse) return cudaErrorNotSupported;
   const bool grid_mode = a.G > 0;
-  void (*kern)(const FlowArgs) = grid_mode ? flow_tc_kernel<true> : flow_tc_kernel<false>;
+  void (*kern)(const FlowArgs) = grid_mode ? flow_tc_kernel<false, true>
+                                           : (inverse ? flow_tc_kernel<true, false> : flow_tc_kernel<false, false>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc);
   if (e != cudaSuccess) return e;
   if (a.n_tiles <= 0) return cudaSuccess;

@@ -23,7 +23,7 @@ AFF_FLOATS = 40
 AFF_INV = 20
 CAFF_FLOATS = 64 + 3 * (64 * 64 + 64) + 16 * 64 + 16
 
-TC_AVAILABLE = True    # csrc/flow_tc.cu: tcgen05 conditioner (forward / grid); the inverse still runs the FP32 kernel
+TC_AVAILABLE = True    # csrc/flow_tc.cu: tcgen05 conditioner (forward, inverse and grid mode)
 TC_WEIGHT_SCALE = 256.0  # fp16 weight planes are stored times 2^8 (kWScale in csrc/flow_tc.cu)
 
 _MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC}
@@ -290,7 +290,6 @@ class Program:
         m = _MODES[mode]
         with torch.cuda.device(self.device):
             if inverse:
-                m = _cabi.RNF_MLP_FP32          # the bisection path exists in the FP32 kernel only (this revision)
                 ns = int(self.lib.rnf_flow_inverse_scratch_floats(self.handle, N))
                 scratch = torch.empty((max(ns, 1),), device=self.device, dtype=torch.float32)
                 _cabi.check(self.lib.rnf_flow_inverse(self.handle, C.c_void_p(R.data_ptr()), N, cp, B, ip, rows_per_image,

@@ -1,0 +1,53 @@
+"""CPU checks of the constants baked into csrc/mobius_fast.cuh (fp32 emulation of the polynomial evaluation)."""
+import re
+import os
+
+import numpy as np
+
+from conftest import ROOT
+
+
+def _coeffs():
+    src = open(os.path.join(ROOT, "rotationnormflow_b200", "csrc", "mobius_fast.cuh")).read()
+    body = src[src.index("atan2_wrapped_fast"):]
+    first = re.search(r"float p = (-?[0-9.e-]+)f;", body).group(1)
+    rest = re.findall(r"p = fmaf\(p, s, (-?[0-9.e-]+)f\);", body)
+    return [float(first)] + [float(v) for v in rest]          # highest degree first
+
+
+def _fma32(a, b, c):
+    return (a.astype(np.float64) * b.astype(np.float64) + np.float64(c)).astype(np.float32)
+
+
+def test_atan_polynomial_accuracy():
+    co = _coeffs()
+    assert len(co) == 9
+    q = np.linspace(0, 1, 1_000_001).astype(np.float32)
+    s = (q.astype(np.float64) * q).astype(np.float32)
+    p = np.full_like(s, np.float32(co[0]))
+    for c in co[1:]:
+        p = _fma32(p, s, np.float32(c))
+    p = (p.astype(np.float64) * s).astype(np.float32)
+    res = (p.astype(np.float64) * q + q).astype(np.float32)
+    err = np.abs(res.astype(np.float64) - np.arctan(q.astype(np.float64)))
+    assert err.max() < 1.0e-7                                   # 1.3 ulp at pi/4
+
+
+def test_octant_reduction_covers_the_circle():
+    """The min/max + three selects of atan2_wrapped_fast reproduce atan2 wrapped to [0, 2 pi) (float64 emulation)."""
+    rng = np.random.default_rng(0)
+    y, x = rng.standard_normal(100000), rng.standard_normal(100000)
+    ay, ax = np.abs(y), np.abs(x)
+    p = np.arctan(np.minimum(ay, ax) / np.maximum(ay, ax))
+    p = np.where(ay > ax, np.pi / 2 - p, p)
+    p = np.where(x < 0, np.pi - p, p)
+    p = np.where(y < 0, 2 * np.pi - p, p)
+    ref = np.arctan2(y, x)
+    ref = np.where(ref >= 0, ref, ref + 2 * np.pi)
+    assert np.abs(p - ref).max() < 1e-12
+
+
+def test_softplus_series_branch():
+    e = np.float64(0.0078125)
+    series = e * (1 - e / 2 + e * e / 3 - e ** 3 / 4)
+    assert abs(series - np.log1p(e)) / np.log1p(e) < 1e-9
