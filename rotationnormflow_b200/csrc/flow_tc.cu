@@ -29,6 +29,10 @@
 namespace rnf {
 namespace {
 
+#ifndef RNF_TC_SUBCHUNKS
+#define RNF_TC_SUBCHUNKS 0
+#endif
+
 constexpr int kThreads = 512;
 constexpr int kRows = 128;                        // rows per tile = TMEM lanes
 constexpr float kWUnscale = 1.0f / 256.0f;
@@ -45,13 +49,13 @@ constexpr int kOffA = 117760;                     // [tile][hi|lo] 128x64 fp16 (
 constexpr int kOffXchg = kOffA + 4 * 16384;       // [tile][half][3][128] fp32
 constexpr int kOffRed = kOffXchg + 2 * 2 * 3 * 128 * 4;   // [tile] reduction scratch (4 warps x (float, int64) + bcast)
 constexpr int kOffBar = kOffRed + 2 * 128;
-constexpr int kOffMisc = kOffBar + 8 * 8;         // tmem base, counters, Mobius offset table
+constexpr int kOffMisc = kOffBar + 8 * 16;         // tmem base, counters, Mobius offset table
 constexpr int kSmemBytes = kOffMisc + 16 + 64 * 8;
 constexpr int kSmemAlloc = kSmemBytes + 1024;     // slack for manual 1024 B alignment
 static_assert(kHidBytes + kLastBytes == kMobFloats * 4, "TC image has the same size as the FP32 image");
 
 // mbarrier slots
-enum { BAR_HID_FULL = 0, BAR_LAST_FULL = 1, BAR_MMA = 2 /* [tile][2] -> 2..5 */ };
+enum { BAR_HID_FULL = 0, BAR_LAST_FULL = 1, BAR_MMA = 2 /* [tile][4] -> 2..9 */ };
 
 // ------------------------------------------------ PTX wrappers ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,11 +71,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(4000u)    // suspend-time hint (ns): fewer polls stealing issue slots from the other tile
       : "memory");
   return ok != 0;
 }
@@ -93,15 +97,21 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::f16 (fp16 operands, fp32 accumulate)
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::f16 (fp16 operands, fp32 accumulate).  The 64-bit shared-memory
+// descriptors are passed as (low word, common high word): only the low word (start address) changes between MMAs, so
+// the single issuing thread spends ~5 instructions per MMA instead of rebuilding both descriptors.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t desc_hi32, uint32_t idesc,
+                                         uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
       "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "r"(a_lo32), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
@@ -137,24 +147,24 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float v[32]) {
 
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor layout:
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=2 (SW128) [61,64)).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
+constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);          // bits [32,64): SBO = 1024 B, version 1, SW128
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=b=F16 (0), K-major both, N>>3 [17,23), M>>4 [24,29)
 __device__ __host__ constexpr uint32_t umma_idesc(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// Issue D[128 x N] = A[128 x 64] . W[N x 64]^T with the 3-product split.  a_* / b_* are shared addresses of the hi / lo
-// fp16 planes (each K-major SW128, 128 B per row).  Small terms are accumulated first.
+// Issue D[128 x N] = A[128 x 64] . W[N x 64]^T with the 3-product split.  a_* / b_* are the descriptor low words of the
+// hi / lo fp16 planes (each K-major SW128, 128 B per row); a K step of 16 elements = 32 B = +2 in the address field.
+// Small terms are accumulated first.
 __device__ __forceinline__ void issue_split_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
                                                  uint32_t idesc) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, umma_desc(a_lo + 32 * k), umma_desc(b_hi + 32 * k), idesc, k > 0);
+  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, kDescHi, idesc, k > 0);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, umma_desc(a_hi + 32 * k), umma_desc(b_lo + 32 * k), idesc, 1);
+  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, kDescHi, idesc, 1);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, umma_desc(a_hi + 32 * k), umma_desc(b_hi + 32 * k), idesc, 1);
+  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, kDescHi, idesc, 1);
 }
 
 __device__ __forceinline__ float sel3(int p, float a, float b, float c) { return p == 0 ? a : (p == 1 ? b : c); }
@@ -201,7 +211,7 @@ struct TileCtx {
   bool elected;    // tile-local thread 0: issues MMAs and weight copies
   uint32_t tmem_d; // TMEM address of this tile's accumulator, lane field = this warp's quarter
   uint32_t bars;   // shared address of the mbarrier array
-  uint32_t par_mma0, par_mma1, par_hid, par_last;   // phase parities
+  uint32_t par_mma0, par_sub, par_hid, par_last;    // phase parities (par_sub: bit i = barrier i of the fc_last sub-chunks)
 };
 
 template <bool INV, bool GRID>
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
   c.row = (warp & 3) * 32 + lane;
   c.elected = (tid & 255) == 0;
   c.bars = smem_u32(smem + kOffBar);
-  c.par_mma0 = c.par_mma1 = c.par_hid = c.par_last = 0;
+  c.par_mma0 = c.par_sub = c.par_hid = c.par_last = 0;
 
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kOffMisc);
   int* s_cnt = reinterpret_cast<int*>(smem + kOffMisc + 4);                // [0] hid, [1] last
@@ -236,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
   if (tid == 0) {
     mbar_init(c.bars + 8 * BAR_HID_FULL, 1);
     mbar_init(c.bars + 8 * BAR_LAST_FULL, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(c.bars + 8 * (BAR_MMA + i), 1);
+    for (int i = 0; i < 8; ++i) mbar_init(c.bars + 8 * (BAR_MMA + i), 1);
     s_cnt[0] = s_cnt[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -264,8 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
 
   uint8_t* a_hi = smem + kOffA + c.tile * 32768;
   uint8_t* a_lo = a_hi + 16384;
-  const uint32_t a_hi_s = smem_u32(a_hi), a_lo_s = smem_u32(a_lo);
-  const uint32_t w_hid_s = smem_u32(smem + kOffHid), w_last_s = smem_u32(smem + kOffLast);
+  const uint32_t a_hi_d = umma_desc_lo(smem_u32(a_hi)), a_lo_d = umma_desc_lo(smem_u32(a_lo));
+  const uint32_t w_hid_d = umma_desc_lo(smem_u32(smem + kOffHid)), w_last_d = umma_desc_lo(smem_u32(smem + kOffLast));
   const float4* sFirst = reinterpret_cast<const float4*>(smem + kOffHid + kHidW);
   const float* sBiasHid = reinterpret_cast<const float*>(smem + kOffHid + kHidW + 1024);
   const float* sBiasLast = reinterpret_cast<const float*>(smem + kOffLast + kLastW);
@@ -274,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
   const float* x_lo = xchg + c.row;
   const float* x_hi = xchg + 384 + c.row;
   const int bar_tile = 1 + c.tile;                   // named barrier of the tile's 256 threads
-  const uint32_t bar_mma0 = c.bars + 8 * (BAR_MMA + 2 * c.tile), bar_mma1 = bar_mma0 + 8;
+  const uint32_t bar_mma0 = c.bars + 8 * (BAR_MMA + 4 * c.tile);   // [0] hidden GEMMs + chunk A0, [1] B0, [2] A1, [3] B1
   const uint32_t tm_stash = c.tmem_d + 64 + 32 * c.half;     // h0 of my 32 hidden columns (free TMEM columns)
   const uint32_t tm_mine = c.tmem_d + 128 * c.half;          // my 128 fc_last columns = 32 mixture components
   int64_t step = 0;                                  // Mobius executions finished by this tile (same on both tiles)
@@ -332,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
         float Wr[17];
 #pragma unroll
         for (int i = 0; i < 17; ++i) Wr[i] = __ldg(W + i);
-        const float loglen = quat_affine(Wr, R);
+        const float loglen = quat_affine_fast(Wr, R);
         if (L.has_ldj) ldj += Wr[16] - 4.0f * loglen;
         continue;
       }
@@ -342,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       Plane P;
       get_col(R, p0, x);
       get_col(R, p1, y);
-      make_frame(x, y, P.r, P.v);
+      make_frame_fast(x, y, P);
       const float* cimg = (L.cond_slot >= 0 && cond_img != nullptr) ? cond_img + (int64_t)L.cond_slot * kH : nullptr;
 
       // the aux block (first layer, biases) arrives with the hidden weights: every thread observes the copy itself
@@ -376,8 +386,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
         named_bar(bar_tile, 256);
         if (c.elected) {
           tc_fence_after();
-          const uint32_t wb = w_hid_s + l * 16384;
-          issue_split_gemm(tmem_base + c.tile * 256, a_hi_s, a_lo_s, wb, wb + 8192, umma_idesc(128, 64));
+          const uint32_t wb = w_hid_d + l * (16384 >> 4);
+          issue_split_gemm(tmem_base + c.tile * 256, a_hi_d, a_lo_d, wb, wb + (8192 >> 4), umma_idesc(128, 64));
           umma_commit(bar_mma0);
         }
         mbar_wait(bar_mma0, c.par_mma0);
@@ -425,22 +435,36 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
           bulk_g2s(smem_u32(smem + kOffHid), src, kHidBytes, c.bars + 8 * BAR_HID_FULL);
         }
         tc_fence_after();
+        // 64-column sub-chunks in the order A0 B0 A1 B1 (A = half 0's columns, B = half 1's), one barrier each, so
+        // both halves start on their first 16 components while the tensor core is still producing the rest
         const uint32_t d = tmem_base + c.tile * 256;
-        issue_split_gemm(d, a_hi_s, a_lo_s, w_last_s, w_last_s + 32768, umma_idesc(128, 128));
+#if RNF_TC_SUBCHUNKS
+#pragma unroll
+        for (int sc = 0; sc < 4; ++sc) {
+          const int col = (sc & 1) * 128 + (sc >> 1) * 64;          // 0, 128, 64, 192
+          issue_split_gemm(d + col, a_hi_d, a_lo_d, w_last_d + col * 8, w_last_d + (32768 >> 4) + col * 8, umma_idesc(128, 64));
+          umma_commit(bar_mma0 + 8 * sc);
+        }
+#else
+        issue_split_gemm(d, a_hi_d, a_lo_d, w_last_d, w_last_d + (32768 >> 4), umma_idesc(128, 128));
         umma_commit(bar_mma0);
-        issue_split_gemm(d + 128, a_hi_s, a_lo_s, w_last_s + 16384, w_last_s + 32768 + 16384, umma_idesc(128, 128));
-        umma_commit(bar_mma1);
+        umma_commit(bar_mma0 + 16);                  // A1 == A0 when the half is one N = 128 chunk
+        issue_split_gemm(d + 128, a_hi_d, a_lo_d, w_last_d + (16384 >> 4), w_last_d + ((32768 + 16384) >> 4), umma_idesc(128, 128));
+        umma_commit(bar_mma0 + 8);
+        umma_commit(bar_mma0 + 24);
+#endif
       }
-      if (c.half == 0) { mbar_wait(bar_mma0, c.par_mma0); } else { mbar_wait(bar_mma1, c.par_mma1); }
-      c.par_mma0 ^= 1;                               // both barriers complete exactly once per layer here
-      c.par_mma1 ^= 1;
-      tc_fence_after();
 
       // ---- mixture of my 32 components, 8 at a time straight from TMEM ----
       float S_sp = 0.0f, S_th = 0.0f, S_f = 0.0f;
       const float zr = dot3(x, P.r), zv = dot3(x, P.v);   // in-plane coordinates of the moving column
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
+        if ((q & 1) == 0) {                          // my sub-chunk q/2: barrier index half + 2*(q/2)
+          const int bi = c.half + (q & 2);
+          mbar_wait(bar_mma0 + 8 * bi, bi == 0 ? c.par_mma0 : ((c.par_sub >> bi) & 1u));
+          tc_fence_after();
+        }
         float acc[32];
         tmem_ld32(tm_mine + 32 * q, acc);
         const float4* b4 = reinterpret_cast<const float4*>(sBiasLast + 128 * c.half + 32 * q);
@@ -463,6 +487,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
         }
         if (INV) tmem_st32(tm_mine + 32 * q, acc);   // prepared parameters stay in my TMEM lane for the bisection
       }
+      c.par_mma0 ^= 1;                               // A0 completed on barrier 0; B0/A1/B1 on barriers 1..3
+      c.par_sub ^= 0xEu;
       // ---- exchange partial sums between the two halves of the row (fixed summation order) ----
       x_mine[0] = S_sp; x_mine[128] = S_th; x_mine[256] = S_f;
       tc_fence_before();
@@ -482,8 +508,9 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       if (!INV) {
         S_th = x_lo[128] + x_hi[128];
         S_f = x_lo[256] + x_hi[256];
-        circle_point(P.r, P.v, S_th / S_sp, nx);
-        ldj += logf(S_f / S_sp);
+        const float inv_sp = rcp_nr(S_sp);
+        circle_point(P.r, P.v, S_th * inv_sp, nx);
+        ldj += logf(S_f * inv_sp);
       } else {
         // target angle of the given column in its own frame (flow/mobiusflow.py:157-167); ~pi by construction
         float ys = atan2f(zv, zr);
@@ -536,7 +563,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
         ldj -= logf((x_lo[0] + x_hi[0]) / S_sp);
       }
       cross3(nx, y, nz);
-      normalize3(nz);
+      normalize3_fast(nz);
       set_col(R, p0, nx);
       set_col(R, p2, nz);
       ++step;

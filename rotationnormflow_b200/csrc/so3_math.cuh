@@ -82,6 +82,64 @@ __device__ __forceinline__ float quat_affine(const float* __restrict__ W, float 
   return logf(len);
 }
 
+
+// ---- single-SFU-instruction variants used by the tensor-core path (flow_tc.cu) -------------------------------------
+// rcp / rsqrt approximations (<= 1 ulp) followed by one Newton step: ~0.5-1 ulp, no IEEE slow path, no branches.
+__device__ __forceinline__ float rcp_nr(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(fmaf(-x, r, 1.0f), r, r);
+}
+__device__ __forceinline__ float rsqrt_nr(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  const float h = 0.5f * x * r;
+  return fmaf(fmaf(-h, r, 0.5f), r, r);               // r (1.5 - 0.5 x r^2)
+}
+__device__ __forceinline__ void normalize3_fast(float a[3]) {
+  const float inv = rsqrt_nr(dot3(a, a));
+  a[0] *= inv; a[1] *= inv; a[2] *= inv;
+}
+
+// calculate_16 without the intermediate normalisations.  quaternion_to_matrix is scale invariant (two_s = 2/|q|^2), so
+// the candidate row of matrix_to_quaternion can stay un-divided: q~ = 2 q_abs q with winning entry q_abs^2 = the radicand,
+// p~ = W q~ = 2 q_abs p, R' = q2m(p~) and log|Wq| = 0.5 log(|p~|^2 / (4 q_abs^2)).  No sqrt, two reciprocals, one log.
+__device__ __forceinline__ float quat_affine_fast(const float* __restrict__ W, float R[9]) {
+  const float m00 = R[0], m01 = R[1], m02 = R[2], m10 = R[3], m11 = R[4], m12 = R[5], m20 = R[6], m21 = R[7], m22 = R[8];
+  const float a0 = 1.0f + m00 + m11 + m22;
+  const float a1 = 1.0f + m00 - m11 - m22;
+  const float a2 = 1.0f - m00 + m11 - m22;
+  const float a3 = 1.0f - m00 - m11 + m22;
+  int best = 0;
+  float am = a0;
+  if (a1 > am) { am = a1; best = 1; }
+  if (a2 > am) { am = a2; best = 2; }
+  if (a3 > am) { am = a3; best = 3; }
+  float q[4];
+  if (best == 0)      { q[0] = am;        q[1] = m21 - m12; q[2] = m02 - m20; q[3] = m10 - m01; }
+  else if (best == 1) { q[0] = m21 - m12; q[1] = am;        q[2] = m10 + m01; q[3] = m02 + m20; }
+  else if (best == 2) { q[0] = m02 - m20; q[1] = m10 + m01; q[2] = am;        q[3] = m12 + m21; }
+  else                { q[0] = m10 - m01; q[1] = m20 + m02; q[2] = m21 + m12; q[3] = am; }
+  float p[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+    p[a] = fmaf(W[4 * a + 3], q[3], fmaf(W[4 * a + 2], q[2], fmaf(W[4 * a + 1], q[1], W[4 * a] * q[0])));
+  const float pp = fmaf(p[3], p[3], fmaf(p[2], p[2], fmaf(p[1], p[1], p[0] * p[0])));
+  const float two_s = 2.0f * rcp_nr(pp);
+  const float r = p[0], i = p[1], j = p[2], k = p[3];
+  const float si = two_s * i, sj = two_s * j, sk = two_s * k;
+  R[0] = 1.0f - fmaf(sj, j, sk * k);
+  R[1] = fmaf(si, j, -sk * r);
+  R[2] = fmaf(si, k, sj * r);
+  R[3] = fmaf(si, j, sk * r);
+  R[4] = 1.0f - fmaf(si, i, sk * k);
+  R[5] = fmaf(sj, k, -si * r);
+  R[6] = fmaf(si, k, -sj * r);
+  R[7] = fmaf(sj, k, si * r);
+  R[8] = 1.0f - fmaf(si, i, sj * j);
+  return 0.5f * logf(pp * rcp_nr(4.0f * am));
+}
+
 __host__ __device__ inline float det3f(float a00, float a01, float a02, float a10, float a11, float a12, float a20,
                                        float a21, float a22) {
   const float d00 = a11 * a22 - a12 * a21;

@@ -8,11 +8,12 @@ from conftest import ROOT
 
 
 def _coeffs():
+    """Coefficients c0..c8 (ascending powers of s = q^2) read back from the Horner evaluation in the header."""
     src = open(os.path.join(ROOT, "rotationnormflow_b200", "csrc", "mobius_fast.cuh")).read()
-    body = src[src.index("atan2_wrapped_fast"):]
+    body = src[src.index("atan2_wrapped_fast"):src.index("struct Plane")]
     first = re.search(r"float p = (-?[0-9.e-]+)f;", body).group(1)
     rest = re.findall(r"p = fmaf\(p, s, (-?[0-9.e-]+)f\);", body)
-    return [float(first)] + [float(v) for v in rest]          # highest degree first
+    return ([float(first)] + [float(v) for v in rest])[::-1]
 
 
 def _fma32(a, b, c):
@@ -24,8 +25,8 @@ def test_atan_polynomial_accuracy():
     assert len(co) == 9
     q = np.linspace(0, 1, 1_000_001).astype(np.float32)
     s = (q.astype(np.float64) * q).astype(np.float32)
-    p = np.full_like(s, np.float32(co[0]))
-    for c in co[1:]:
+    p = np.full_like(s, np.float32(co[-1]))
+    for c in co[-2::-1]:
         p = _fma32(p, s, np.float32(c))
     p = (p.astype(np.float64) * s).astype(np.float32)
     res = (p.astype(np.float64) * q + q).astype(np.float32)
