@@ -265,6 +265,32 @@ def main():
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = world * G * B / (float(e2e_t.item()) / args.steps)
 
+    # secondary figure of the metric: sampling = Flow.inverse (BASELINE configs[3], SYMSOL-II stack, F=512), scaled to
+    # 64 images x 32768 base samples per rank so the default run stays short; device-timed, not part of `value`.
+    import rotationnormflow_b200 as rnf2
+    torch.manual_seed(0); np.random.seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        flow_s = rnf2.get_flow(rnf2.load_config("symsol2")).to(dev).eval()
+    n_img_s, n_per = 64, 32768
+    base = rgrid.generate_queries(n_img_s * n_per, "random", device=dev)
+    feat_s = torch.relu(torch.randn(n_img_s, 512, generator=torch.Generator().manual_seed(5))).to(dev)
+    idx_s = torch.arange(n_img_s * n_per, device=dev, dtype=torch.int32) // n_per
+    samp_ms = []
+    with torch.no_grad():
+        for i in range(2 + 3):
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            Rs, ls = flow_s.inverse(base, feat_s, feature_index=idx_s, mlp_mode=mode)
+            s1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                samp_ms.append(s0.elapsed_time(s1))
+    samp_t = torch.tensor([statistics.mean(samp_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(samp_t, op=dist.ReduceOp.MAX)
+    sampling = {"value": world * n_img_s * n_per / (float(samp_t.item()) * 1e-3), "unit": "samples/s", "ms": float(samp_t.item()),
+                "config": f"symsol2.yml (F=512, 42 layers) Flow.inverse, {n_img_s} images x {n_per} samples per rank (BASELINE configs[3] scaled down)"}
+
     pk = peaks()
     kt = statistics.mean(k_ms) * 1e-3
     rot_per_launch = G * B
@@ -296,6 +322,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(feat_host.numel() * 4),
                 "d2h_bytes_per_step": int(B * (4 + 8 + 4))},
         "gpu_launches": int(args.steps * (2 + 2)),
+        "sampling": sampling,
         "wall_s_timed_region": t_wall,
         "check": {"argmax0": int(res[1][0]), "log_norm0": float(res[2][0])},
     }

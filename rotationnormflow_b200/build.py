@@ -34,7 +34,7 @@ def _digest() -> str:
             h.update(n.encode())
             with open(p, "rb") as f:
                 h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + os.environ.get("RNF_NVCC_EXTRA", "")).encode())
     return h.hexdigest()
 
 
@@ -48,7 +48,8 @@ def up_to_date() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    extra = os.environ.get("RNF_NVCC_EXTRA", "").split()          # e.g. -DRNF_TC_TRACE=1 for the phase-timeline debug build
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(CSRC, ".build_log"), "w") as f:

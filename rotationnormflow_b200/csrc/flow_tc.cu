@@ -29,33 +29,50 @@
 namespace rnf {
 namespace {
 
-#ifndef RNF_TC_SUBCHUNKS
-#define RNF_TC_SUBCHUNKS 0
+#ifndef RNF_TC_WAIT_HINT_NS
+#define RNF_TC_WAIT_HINT_NS 0
+#endif
+
+#ifndef RNF_TC_TURN_RELEASE
+#define RNF_TC_TURN_RELEASE -1     // >= 0: explicit ping-pong, GEMM index (0..2 hidden, 3 fc_last) whose issue hands the turn to the other tile (measured: no gain)
+#endif
+
+#ifndef RNF_TC_TRACE
+#define RNF_TC_TRACE 0
+#endif
+#if RNF_TC_TRACE
+#define TRACE(i) do { if (tr_on) tr[(i)] = clock64(); } while (0)
+#else
+#define TRACE(i) do { } while (0)
 #endif
 
 constexpr int kThreads = 512;
 constexpr int kRows = 128;                        // rows per tile = TMEM lanes
 constexpr float kWUnscale = 1.0f / 256.0f;
 
-// ---- shared-memory image (bytes from a 1024-aligned base); the first two regions mirror the packed global image ----
-constexpr int kHidW = 3 * 2 * 8192;               // [layer][hi|lo] 64x64 fp16, K-major SW128
-constexpr int kHidAux = 1024 + 768;               // first[64][4] fp32 ; b1,b2,b3 fp32
-constexpr int kHidBytes = kHidW + kHidAux;        // 50944
+// ---- shared-memory image (bytes from a 1024-aligned base).  The packed global image of one Mobius conditioner is
+//      [W1 | W2 | W3 : each (hi 64x64, lo 64x64) fp16 SW128][W4 : hi 256x64, lo 256x64][aux : first[64][4], b1..b3, b4' fp32]
+//      and every piece is brought in by its own bulk copy as soon as its previous contents are dead. ----
+constexpr int kW1Bytes = 2 * 8192;                // one hidden layer: hi | lo planes
+constexpr int kHidW = 3 * kW1Bytes;               // 49152
 constexpr int kLastW = 2 * 32768;                 // [hi|lo] 256x64 fp16
-constexpr int kLastBytes = kLastW + 1024;         // + permuted fc_last bias (fp32)
-constexpr int kOffHid = 0;
-constexpr int kOffLast = 51200;
-constexpr int kOffA = 117760;                     // [tile][hi|lo] 128x64 fp16 (16 KB each)
+constexpr int kAuxBytes = 1024 + 768 + 1024;      // first[64][4] ; b1,b2,b3 ; permuted fc_last bias   (fp32)
+constexpr int kAuxStride = 3072;
+constexpr int kOffW = 0;
+constexpr int kOffLastW = kHidW;                  // 49152
+constexpr int kOffAux = kOffLastW + kLastW;       // 114688, double buffered (layer parity)
+constexpr int kOffA = kOffAux + 2 * kAuxStride;   // 120832 = 118 * 1024 : [tile][hi|lo] 128x64 fp16 (16 KB each)
 constexpr int kOffXchg = kOffA + 4 * 16384;       // [tile][half][3][128] fp32
-constexpr int kOffRed = kOffXchg + 2 * 2 * 3 * 128 * 4;   // [tile] reduction scratch (4 warps x (float, int64) + bcast)
+constexpr int kOffRed = kOffXchg + 2 * 2 * 3 * 128 * 4;   // [tile] reduction scratch
 constexpr int kOffBar = kOffRed + 2 * 128;
-constexpr int kOffMisc = kOffBar + 8 * 16;         // tmem base, counters, Mobius offset table
-constexpr int kSmemBytes = kOffMisc + 16 + 64 * 8;
+constexpr int kOffMisc = kOffBar + 8 * 16;        // tmem base, counters, Mobius offset table
+constexpr int kSmemBytes = kOffMisc + 32 + 64 * 8;
 constexpr int kSmemAlloc = kSmemBytes + 1024;     // slack for manual 1024 B alignment
-static_assert(kHidBytes + kLastBytes == kMobFloats * 4, "TC image has the same size as the FP32 image");
+static_assert(kHidW + kLastW + kAuxBytes == kMobFloats * 4, "TC image has the same size as the FP32 image");
+static_assert(kOffA % 1024 == 0 && kOffLastW % 1024 == 0, "UMMA SW128 tiles need 1024 B alignment");
 
 // mbarrier slots
-enum { BAR_HID_FULL = 0, BAR_LAST_FULL = 1, BAR_MMA = 2 /* [tile][4] -> 2..9 */ };
+enum { BAR_W_FULL = 0 /* W1,W2,W3,W4 */, BAR_AUX_FULL = 4 /* [2] */, BAR_MMA = 6 /* [tile][2] */, BAR_COUNT = 10 };
 
 // ------------------------------------------------ PTX wrappers ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,11 +88,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
+#if RNF_TC_WAIT_HINT_NS > 0
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+#else
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#endif
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(4000u)    // suspend-time hint (ns): fewer polls stealing issue slots from the other tile
+      : "r"(bar), "r"(parity), "r"((uint32_t)RNF_TC_WAIT_HINT_NS)   // suspend-time hint: fewer polls stealing issue slots
       : "memory");
   return ok != 0;
 }
@@ -93,6 +114,9 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -211,7 +235,7 @@ struct TileCtx {
   bool elected;    // tile-local thread 0: issues MMAs and weight copies
   uint32_t tmem_d; // TMEM address of this tile's accumulator, lane field = this warp's quarter
   uint32_t bars;   // shared address of the mbarrier array
-  uint32_t par_mma0, par_sub, par_hid, par_last;    // phase parities (par_sub: bit i = barrier i of the fc_last sub-chunks)
+  uint32_t par_mma0, par_mma1, par_w;               // phase parities (par_w: bit l = weight region l, elected thread only)
 };
 
 template <bool INV, bool GRID>
@@ -228,11 +252,11 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
   c.row = (warp & 3) * 32 + lane;
   c.elected = (tid & 255) == 0;
   c.bars = smem_u32(smem + kOffBar);
-  c.par_mma0 = c.par_sub = c.par_hid = c.par_last = 0;
+  c.par_mma0 = c.par_mma1 = c.par_w = 0;
 
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kOffMisc);
-  int* s_cnt = reinterpret_cast<int*>(smem + kOffMisc + 4);                // [0] hid, [1] last
-  long long* s_moff = reinterpret_cast<long long*>(smem + kOffMisc + 16);  // w_off_tc of Mobius layers, execution order
+  int* s_cnt = reinterpret_cast<int*>(smem + kOffMisc + 4);                // consumers done: [0..2] W1..W3, [3] W4, [4] aux
+  long long* s_moff = reinterpret_cast<long long*>(smem + kOffMisc + 32);  // w_off_tc of Mobius layers, execution order
 
   // ---- one-time setup -------------------------------------------------------------------------------------------------
   int n_mob = 0;
@@ -244,10 +268,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
     }
   }
   if (tid == 0) {
-    mbar_init(c.bars + 8 * BAR_HID_FULL, 1);
-    mbar_init(c.bars + 8 * BAR_LAST_FULL, 1);
-    for (int i = 0; i < 8; ++i) mbar_init(c.bars + 8 * (BAR_MMA + i), 1);
-    s_cnt[0] = s_cnt[1] = 0;
+    for (int i = 0; i < BAR_COUNT; ++i) mbar_init(c.bars + 8 * i, 1);
+    for (int i = 0; i < 5; ++i) s_cnt[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -264,30 +286,39 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
   const int64_t my_items = blockIdx.x < n_pairs ? (n_pairs - 1 - blockIdx.x) / gridDim.x + 1 : 0;
   const int64_t total_steps = my_items * n_mob;     // Mobius layer executions of this CTA
   const uint8_t* wbytes = reinterpret_cast<const uint8_t*>(a.weights);
-  if (tid == 0 && total_steps > 0) {                // prime both weight regions with the first Mobius layer
-    const uint8_t* src = wbytes + s_moff[0] * 4;
-    mbar_expect_tx(c.bars + 8 * BAR_HID_FULL, kHidBytes);
-    bulk_g2s(smem_u32(smem + kOffHid), src, kHidBytes, c.bars + 8 * BAR_HID_FULL);
-    mbar_expect_tx(c.bars + 8 * BAR_LAST_FULL, kLastBytes);
-    bulk_g2s(smem_u32(smem + kOffLast), src + kHidBytes, kLastBytes, c.bars + 8 * BAR_LAST_FULL);
+  // One bulk copy per piece of a layer image; `piece` 0..2 = W1..W3, 3 = W4, 4 = aux (into buffer `abuf`).
+  auto load_piece = [&](int64_t mob_step, int piece, int abuf) {
+    const uint8_t* src = wbytes + s_moff[mob_step % n_mob] * 4;
+    uint32_t dst, bytes, bar;
+    if (piece < 3) { src += piece * kW1Bytes; dst = kOffW + piece * kW1Bytes; bytes = kW1Bytes; bar = BAR_W_FULL + piece; }
+    else if (piece == 3) { src += kHidW; dst = kOffLastW; bytes = kLastW; bar = BAR_W_FULL + 3; }
+    else { src += kHidW + kLastW; dst = kOffAux + abuf * kAuxStride; bytes = kAuxBytes; bar = BAR_AUX_FULL + abuf; }
+    mbar_expect_tx(c.bars + 8 * bar, bytes);
+    bulk_g2s(smem_u32(smem + dst), src, bytes, c.bars + 8 * bar);
+  };
+  if (tid == 0 && total_steps > 0) {                // prime every region with the first Mobius layer(s)
+    for (int piece = 0; piece < 4; ++piece) load_piece(0, piece, 0);
+    load_piece(0, 4, 0);
+    if (total_steps > 1) load_piece(1, 4, 1);
   }
 
   uint8_t* a_hi = smem + kOffA + c.tile * 32768;
   uint8_t* a_lo = a_hi + 16384;
   const uint32_t a_hi_d = umma_desc_lo(smem_u32(a_hi)), a_lo_d = umma_desc_lo(smem_u32(a_lo));
-  const uint32_t w_hid_d = umma_desc_lo(smem_u32(smem + kOffHid)), w_last_d = umma_desc_lo(smem_u32(smem + kOffLast));
-  const float4* sFirst = reinterpret_cast<const float4*>(smem + kOffHid + kHidW);
-  const float* sBiasHid = reinterpret_cast<const float*>(smem + kOffHid + kHidW + 1024);
-  const float* sBiasLast = reinterpret_cast<const float*>(smem + kOffLast + kLastW);
+  const uint32_t w_hid_d = umma_desc_lo(smem_u32(smem + kOffW)), w_last_d = umma_desc_lo(smem_u32(smem + kOffLastW));
   float* xchg = reinterpret_cast<float*>(smem + kOffXchg) + c.tile * (2 * 3 * 128);   // [half][slot 0..2][row]
   float* x_mine = xchg + c.half * 384 + c.row;
   const float* x_lo = xchg + c.row;
   const float* x_hi = xchg + 384 + c.row;
   const int bar_tile = 1 + c.tile;                   // named barrier of the tile's 256 threads
-  const uint32_t bar_mma0 = c.bars + 8 * (BAR_MMA + 4 * c.tile);   // [0] hidden GEMMs + chunk A0, [1] B0, [2] A1, [3] B1
+  const uint32_t bar_mma0 = c.bars + 8 * (BAR_MMA + 2 * c.tile), bar_mma1 = bar_mma0 + 8;   // hidden GEMMs + chunk A | chunk B
   const uint32_t tm_stash = c.tmem_d + 64 + 32 * c.half;     // h0 of my 32 hidden columns (free TMEM columns)
   const uint32_t tm_mine = c.tmem_d + 128 * c.half;          // my 128 fc_last columns = 32 mixture components
   int64_t step = 0;                                  // Mobius executions finished by this tile (same on both tiles)
+  // Ping-pong of the two tiles: the MLP chain of one tile (latency bound: four dependent GEMM round trips) is made to run
+  // against the mixture arithmetic of the other (issue bound).  Named barrier 5 + t = "tile t may start its chain".
+  const int turn_mine = 5 + c.tile, turn_other = 6 - c.tile;
+  if (RNF_TC_TURN_RELEASE >= 0 && c.tile == 1) named_arrive(5, 512);
 
   for (int64_t item = 0; item < my_items; ++item) {
     const int64_t tile_idx = 2 * (blockIdx.x + item * (int64_t)gridDim.x) + c.tile;
@@ -355,9 +386,21 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       make_frame_fast(x, y, P);
       const float* cimg = (L.cond_slot >= 0 && cond_img != nullptr) ? cond_img + (int64_t)L.cond_slot * kH : nullptr;
 
-      // the aux block (first layer, biases) arrives with the hidden weights: every thread observes the copy itself
-      mbar_wait(c.bars + 8 * BAR_HID_FULL, c.par_hid);
-      c.par_hid ^= 1;
+#if RNF_TC_TRACE
+      const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && c.elected && step >= 40 && step < 48;
+      long long* tr = a.trace + ((c.tile * 8 + (step - 40)) * 32);
+#endif
+      TRACE(0);
+      if (RNF_TC_TURN_RELEASE >= 0) named_bar(turn_mine, 512);
+      TRACE(1);
+      // fp32 side data of this layer (first-layer columns, biases): double buffered on the layer parity, every thread
+      // observes the bulk copy itself
+      const int abuf = (int)(step & 1);
+      mbar_wait(c.bars + 8 * (BAR_AUX_FULL + abuf), (uint32_t)((step >> 1) & 1));
+      const uint8_t* aux = smem + kOffAux + abuf * kAuxStride;
+      const float4* sFirst = reinterpret_cast<const float4*>(aux);
+      const float* sBiasHid = reinterpret_cast<const float*>(aux + 1024);
+      const float* sBiasLast = reinterpret_cast<const float*>(aux + 1792);
 
       // ---- first conditioner layer for my 32 columns; pre-activation stashed in TMEM for the residual ----
       {
@@ -378,21 +421,29 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
         store_a_operand(a_hi, a_lo, c.row, c.half, act);
         tmem_st32(tm_stash, h0);
       }
+      TRACE(2);
       // ---- three hidden layers on the tensor core ----
 #pragma unroll 1
       for (int l = 0; l < 3; ++l) {
         fence_proxy_async();
         tc_fence_before();
         named_bar(bar_tile, 256);
+        TRACE(3 + 4 * l);
+        if (RNF_TC_TURN_RELEASE == l) named_arrive(turn_other, 512);
         if (c.elected) {
+          mbar_wait(c.bars + 8 * (BAR_W_FULL + l), (c.par_w >> l) & 1u);
           tc_fence_after();
-          const uint32_t wb = w_hid_d + l * (16384 >> 4);
+          const uint32_t wb = w_hid_d + l * (kW1Bytes >> 4);
           issue_split_gemm(tmem_base + c.tile * 256, a_hi_d, a_lo_d, wb, wb + (8192 >> 4), umma_idesc(128, 64));
           umma_commit(bar_mma0);
         }
+        TRACE(4 + 4 * l);
         mbar_wait(bar_mma0, c.par_mma0);
         c.par_mma0 ^= 1;
         tc_fence_after();
+        TRACE(5 + 4 * l);
+        // W_l is dead once BOTH tiles' GEMM l has completed: the second tile to get here refills it for the next layer
+        if (c.elected && (atomicAdd(&s_cnt[l], 1) & 1) && step + 1 < total_steps) load_piece(step + 1, l, 0);
         float acc[32];
         tmem_ld32(c.tmem_d + 32 * c.half, acc);
         const float4* bias4 = reinterpret_cast<const float4*>(sBiasHid + 64 * l + 32 * c.half);
@@ -418,53 +469,35 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
           }
         }
         store_a_operand(a_hi, a_lo, c.row, c.half, acc);
+        TRACE(6 + 4 * l);
       }
       // ---- fc_last: two N = 128 chunks, own barrier each ----
       fence_proxy_async();
       tc_fence_before();
       named_bar(bar_tile, 256);
-      mbar_wait(c.bars + 8 * BAR_LAST_FULL, c.par_last);   // weights for the MMA, permuted bias for every thread
-      c.par_last ^= 1;
+      TRACE(15);
+      if (RNF_TC_TURN_RELEASE == 3) named_arrive(turn_other, 512);
       if (c.elected) {
-        // The hidden region (weights + biases) is free once every thread of BOTH tiles is past the third hidden
-        // epilogue (the barrier above): the second tile to get here refills it for the next Mobius layer.
-        const int old = atomicAdd(&s_cnt[0], 1);
-        if ((old & 1) && step + 1 < total_steps) {
-          const uint8_t* src = wbytes + s_moff[(step + 1) % n_mob] * 4;
-          mbar_expect_tx(c.bars + 8 * BAR_HID_FULL, kHidBytes);
-          bulk_g2s(smem_u32(smem + kOffHid), src, kHidBytes, c.bars + 8 * BAR_HID_FULL);
-        }
+        mbar_wait(c.bars + 8 * (BAR_W_FULL + 3), (c.par_w >> 3) & 1u);
         tc_fence_after();
-        // 64-column sub-chunks in the order A0 B0 A1 B1 (A = half 0's columns, B = half 1's), one barrier each, so
-        // both halves start on their first 16 components while the tensor core is still producing the rest
         const uint32_t d = tmem_base + c.tile * 256;
-#if RNF_TC_SUBCHUNKS
-#pragma unroll
-        for (int sc = 0; sc < 4; ++sc) {
-          const int col = (sc & 1) * 128 + (sc >> 1) * 64;          // 0, 128, 64, 192
-          issue_split_gemm(d + col, a_hi_d, a_lo_d, w_last_d + col * 8, w_last_d + (32768 >> 4) + col * 8, umma_idesc(128, 64));
-          umma_commit(bar_mma0 + 8 * sc);
-        }
-#else
         issue_split_gemm(d, a_hi_d, a_lo_d, w_last_d, w_last_d + (32768 >> 4), umma_idesc(128, 128));
         umma_commit(bar_mma0);
-        umma_commit(bar_mma0 + 16);                  // A1 == A0 when the half is one N = 128 chunk
         issue_split_gemm(d + 128, a_hi_d, a_lo_d, w_last_d + (16384 >> 4), w_last_d + ((32768 + 16384) >> 4), umma_idesc(128, 128));
-        umma_commit(bar_mma0 + 8);
-        umma_commit(bar_mma0 + 24);
-#endif
+        umma_commit(bar_mma1);
       }
+      TRACE(16);
+      if (c.half == 0) { mbar_wait(bar_mma0, c.par_mma0); } else { mbar_wait(bar_mma1, c.par_mma1); }
+      c.par_mma0 ^= 1;                               // both barriers complete exactly once here
+      c.par_mma1 ^= 1;
+      tc_fence_after();
 
+      TRACE(17);
       // ---- mixture of my 32 components, 8 at a time straight from TMEM ----
       float S_sp = 0.0f, S_th = 0.0f, S_f = 0.0f;
       const float zr = dot3(x, P.r), zv = dot3(x, P.v);   // in-plane coordinates of the moving column
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
-        if ((q & 1) == 0) {                          // my sub-chunk q/2: barrier index half + 2*(q/2)
-          const int bi = c.half + (q & 2);
-          mbar_wait(bar_mma0 + 8 * bi, bi == 0 ? c.par_mma0 : ((c.par_sub >> bi) & 1u));
-          tc_fence_after();
-        }
         float acc[32];
         tmem_ld32(tm_mine + 32 * q, acc);
         const float4* b4 = reinterpret_cast<const float4*>(sBiasLast + 128 * c.half + 32 * q);
@@ -487,22 +520,21 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
         }
         if (INV) tmem_st32(tm_mine + 32 * q, acc);   // prepared parameters stay in my TMEM lane for the bisection
       }
-      c.par_mma0 ^= 1;                               // A0 completed on barrier 0; B0/A1/B1 on barriers 1..3
-      c.par_sub ^= 0xEu;
+      TRACE(18);
+      // W4 is dead once both chunks of BOTH tiles have completed (the elected thread sits in half 0: check chunk B too)
+      if (c.elected) {
+        mbar_wait(bar_mma1, c.par_mma1 ^ 1u);
+        if ((atomicAdd(&s_cnt[3], 1) & 1) && step + 1 < total_steps) load_piece(step + 1, 3, 0);
+        c.par_w ^= 0xFu;
+      }
       // ---- exchange partial sums between the two halves of the row (fixed summation order) ----
       x_mine[0] = S_sp; x_mine[128] = S_th; x_mine[256] = S_f;
       tc_fence_before();
       named_bar(bar_tile, 256);
-      // Past this barrier every thread of the tile is done with the fc_last bias and both MMA chunks have completed
-      // (half 1 waited for chunk B): the second tile to get here refills the fc_last region.
-      if (c.elected) {
-        const int old = atomicAdd(&s_cnt[1], 1);
-        if ((old & 1) && step + 1 < total_steps) {
-          const uint8_t* src = wbytes + s_moff[(step + 1) % n_mob] * 4 + kHidBytes;
-          mbar_expect_tx(c.bars + 8 * BAR_LAST_FULL, kLastBytes);
-          bulk_g2s(smem_u32(smem + kOffLast), src, kLastBytes, c.bars + 8 * BAR_LAST_FULL);
-        }
-      }
+      // Past this barrier every thread of the tile is done with this layer's aux buffer: when both tiles are, it is
+      // refilled with the side data of the layer after next.
+      TRACE(19);
+      if (c.elected && (atomicAdd(&s_cnt[4], 1) & 1) && step + 2 < total_steps) load_piece(step + 2, 4, abuf);
       S_sp = x_lo[0] + x_hi[0];
       float nx[3], nz[3];
       if (!INV) {
@@ -566,6 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       normalize3_fast(nz);
       set_col(R, p0, nx);
       set_col(R, p2, nz);
+      TRACE(20);
       ++step;
     }
 

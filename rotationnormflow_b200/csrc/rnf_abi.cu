@@ -23,6 +23,8 @@ int cuda_fail(cudaError_t e, const char* what) {
   return (int)e;
 }
 
+long long* g_trace = nullptr;
+
 bool valid_mode(int m) { return m == RNF_MLP_FP32 || m == RNF_MLP_TC; }
 
 }  // namespace
@@ -33,6 +35,9 @@ bool flow_tc_supported(const rnf_flow* f);
 }  // namespace rnf
 
 extern "C" {
+
+// debug hook (not part of the ABI header): device buffer that -DRNF_TC_TRACE builds fill with clock64() stamps
+void rnf_debug_set_trace(long long* dev_ptr) { g_trace = dev_ptr; }
 
 int rnf_abi_version(void) { return RNF_ABI_VERSION; }
 
@@ -150,6 +155,7 @@ static int run_rows(rnf_flow* f, bool inverse, const float* R_in, int64_t N, con
   a.R_out = R_out;
   a.ldj_out = ldj_out;
   a.scratch = scratch;
+  a.trace = g_trace;
   cudaError_t e;
   if (mlp_mode == RNF_MLP_TC) {
     if (!rnf::flow_tc_supported(f)) return fail(RNF_ESTATE, "%s: model was packed without the tensor-core weight image", who);
@@ -216,6 +222,7 @@ int rnf_grid_logprob(rnf_flow* f, const float* grid_dev, int64_t G, int64_t g_in
   a.fisher_c = fisher_c_dev;
   a.logp_out = logp_out_dev;
   a.part = part_dev;
+  a.trace = g_trace;
   cudaError_t e;
   if (mlp_mode == RNF_MLP_TC) {
     if (!rnf::flow_tc_supported(f)) return fail(RNF_ESTATE, "rnf_grid_logprob: model was packed without the tensor-core weight image");

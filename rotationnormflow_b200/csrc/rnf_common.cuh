@@ -64,6 +64,7 @@ struct FlowArgs {
   const float* fisher_c;
   float* logp_out;
   float* part;
+  long long* trace;   // debug builds (-DRNF_TC_TRACE): per-phase clock64() stamps of CTA 0, else unused
 };
 
 }  // namespace rnf

@@ -93,19 +93,19 @@ def _split_fp16(W: np.ndarray):
 
 def pack_mobius_tc(cond_sd: dict) -> np.ndarray:
     """Tensor-core image of one Mobius conditioner = the exact shared-memory image of csrc/flow_tc.cu:
-    [3 x (hi 64x64, lo 64x64) fp16 SW128 | first[64][4] fp32 | b1,b2,b3 fp32 | (hi 256x64, lo 256x64) fp16 SW128 | b4' fp32]
+    [3 x (hi 64x64, lo 64x64) fp16 SW128 | (hi 256x64, lo 256x64) fp16 SW128 | first[64][4], b1,b2,b3, b4' fp32]
     returned as float32 words (MOB_FLOATS of them)."""
     W0, b0 = _np(cond_sd["fc_first.weight"]), _np(cond_sd["fc_first.bias"])
     parts = []
     for j in (1, 3, 5):
         hi, lo = _split_fp16(_np(cond_sd[f"layers.{j}.weight"]))          # nn.Linear weight is [out=N, in=K]: K-major
         parts += [_umma_k_major_sw128(hi).view(np.float32), _umma_k_major_sw128(lo).view(np.float32)]
-    parts.append(np.concatenate([W0[:, :3], b0[:, None]], axis=1).astype(np.float32).reshape(-1))
-    for j in (1, 3, 5):
-        parts.append(_np(cond_sd[f"layers.{j}.bias"]))
     perm = _last_layer_perm(K_SEGMENTS)
     hi, lo = _split_fp16(_np(cond_sd["fc_last.weight"])[perm])
     parts += [_umma_k_major_sw128(hi).view(np.float32), _umma_k_major_sw128(lo).view(np.float32)]
+    parts.append(np.concatenate([W0[:, :3], b0[:, None]], axis=1).astype(np.float32).reshape(-1))
+    for j in (1, 3, 5):
+        parts.append(_np(cond_sd[f"layers.{j}.bias"]))
     parts.append(_np(cond_sd["fc_last.bias"])[perm])
     blk = np.concatenate(parts).astype(np.float32, copy=False)
     assert blk.size == MOB_FLOATS
