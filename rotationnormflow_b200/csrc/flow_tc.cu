@@ -21,17 +21,10 @@
 //
 // Quaternion affine layers, grid mode (offset, Fisher base term, per-tile max / arg-max / sum-exp) and the row <-> image
 // mapping are identical to flow_v1.cu.
-#include <cuda_fp16.h>
-
-#include "mobius_fast.cuh"
-#include "rnf_common.cuh"
+#include "tc_common.cuh"
 
 namespace rnf {
 namespace {
-
-#ifndef RNF_TC_WAIT_HINT_NS
-#define RNF_TC_WAIT_HINT_NS 0
-#endif
 
 #ifndef RNF_TC_TURN_RELEASE
 #define RNF_TC_TURN_RELEASE -1     // >= 0: explicit ping-pong, GEMM index (0..2 hidden, 3 fc_last) whose issue hands the turn to the other tile (measured: no gain)
@@ -48,16 +41,10 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kRows = 128;                        // rows per tile = TMEM lanes
-constexpr float kWUnscale = 1.0f / 256.0f;
 
 // ---- shared-memory image (bytes from a 1024-aligned base).  The packed global image of one Mobius conditioner is
 //      [W1 | W2 | W3 : each (hi 64x64, lo 64x64) fp16 SW128][W4 : hi 256x64, lo 256x64][aux : first[64][4], b1..b3, b4' fp32]
 //      and every piece is brought in by its own bulk copy as soon as its previous contents are dead. ----
-constexpr int kW1Bytes = 2 * 8192;                // one hidden layer: hi | lo planes
-constexpr int kHidW = 3 * kW1Bytes;               // 49152
-constexpr int kLastW = 2 * 32768;                 // [hi|lo] 256x64 fp16
-constexpr int kAuxBytes = 1024 + 768 + 1024;      // first[64][4] ; b1,b2,b3 ; permuted fc_last bias   (fp32)
-constexpr int kAuxStride = 3072;
 constexpr int kOffW = 0;
 constexpr int kOffLastW = kHidW;                  // 49152
 constexpr int kOffAux = kOffLastW + kLastW;       // 114688, double buffered (layer parity)
@@ -68,143 +55,10 @@ constexpr int kOffBar = kOffRed + 2 * 128;
 constexpr int kOffMisc = kOffBar + 8 * 16;        // tmem base, counters, Mobius offset table
 constexpr int kSmemBytes = kOffMisc + 32 + 64 * 8;
 constexpr int kSmemAlloc = kSmemBytes + 1024;     // slack for manual 1024 B alignment
-static_assert(kHidW + kLastW + kAuxBytes == kMobFloats * 4, "TC image has the same size as the FP32 image");
 static_assert(kOffA % 1024 == 0 && kOffLastW % 1024 == 0, "UMMA SW128 tiles need 1024 B alignment");
 
 // mbarrier slots
 enum { BAR_W_FULL = 0 /* W1,W2,W3,W4 */, BAR_AUX_FULL = 4 /* [2] */, BAR_MMA = 6 /* [tile][2] */, BAR_COUNT = 10 };
-
-// ------------------------------------------------ PTX wrappers ---------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-#if RNF_TC_WAIT_HINT_NS > 0
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-#else
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-#endif
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"((uint32_t)RNF_TC_WAIT_HINT_NS)   // suspend-time hint: fewer polls stealing issue slots
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void named_bar(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void named_arrive(int id, int nthreads) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::f16 (fp16 operands, fp32 accumulate).  The 64-bit shared-memory
-// descriptors are passed as (low word, common high word): only the low word (start address) changes between MMAs, so
-// the single issuing thread spends ~5 instructions per MMA instead of rebuilding both descriptors.
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t desc_hi32, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      ".reg .b64 da, db;\n"
-      "setp.ne.b32 p, %5, 0;\n"
-      "mov.b64 da, {%1, %3};\n"
-      "mov.b64 db, {%2, %3};\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_lo32), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
-  uint32_t* u = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
-        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
-        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// the inverse: 32 registers -> 32 consecutive fp32 columns of the thread's own TMEM lane (private scratch)
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float v[32]) {
-  const uint32_t* u = reinterpret_cast<const uint32_t*>(v);
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]),
-      "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]), "r"(u[16]), "r"(u[17]), "r"(u[18]),
-      "r"(u[19]), "r"(u[20]), "r"(u[21]), "r"(u[22]), "r"(u[23]), "r"(u[24]), "r"(u[25]), "r"(u[26]), "r"(u[27]),
-      "r"(u[28]), "r"(u[29]), "r"(u[30]), "r"(u[31])
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor layout:
-// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=2 (SW128) [61,64)).
-constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);          // bits [32,64): SBO = 1024 B, version 1, SW128
-__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
-// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=b=F16 (0), K-major both, N>>3 [17,23), M>>4 [24,29)
-__device__ __host__ constexpr uint32_t umma_idesc(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// Issue D[128 x N] = A[128 x 64] . W[N x 64]^T with the 3-product split.  a_* / b_* are the descriptor low words of the
-// hi / lo fp16 planes (each K-major SW128, 128 B per row); a K step of 16 elements = 32 B = +2 in the address field.
-// Small terms are accumulated first.
-__device__ __forceinline__ void issue_split_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                                 uint32_t idesc) {
-#pragma unroll
-  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, kDescHi, idesc, k > 0);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, kDescHi, idesc, 1);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, kDescHi, idesc, 1);
-}
-
-__device__ __forceinline__ float sel3(int p, float a, float b, float c) { return p == 0 ? a : (p == 1 ? b : c); }
-__device__ __forceinline__ void get_col(const float R[9], int p, float o[3]) {
-  o[0] = sel3(p, R[0], R[1], R[2]);
-  o[1] = sel3(p, R[3], R[4], R[5]);
-  o[2] = sel3(p, R[6], R[7], R[8]);
-}
-__device__ __forceinline__ void set_col(float R[9], int p, const float c[3]) {
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    R[3 * i + 0] = p == 0 ? c[i] : R[3 * i + 0];
-    R[3 * i + 1] = p == 1 ? c[i] : R[3 * i + 1];
-    R[3 * i + 2] = p == 2 ? c[i] : R[3 * i + 2];
-  }
-}
 
 // Split 32 non-negative fp32 activations (columns 32h .. 32h+31 of row r) into fp16 hi / lo and store them into the
 // K-major SW128 A operand: element (r, k) lives at (r/8)*1024 + (r%8)*128 + ((k/8) ^ (r%8))*16 + (k%8)*2.

@@ -25,12 +25,13 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 long long* g_trace = nullptr;
 
-bool valid_mode(int m) { return m == RNF_MLP_FP32 || m == RNF_MLP_TC; }
+bool valid_mode(int m) { return m == RNF_MLP_FP32 || m == RNF_MLP_TC || m == RNF_MLP_TC_PAIR; }
 
 }  // namespace
 
 namespace rnf {
 cudaError_t launch_flow_tc(const FlowArgs& a, bool inverse, int sm_count, cudaStream_t st);
+cudaError_t launch_flow_tc2(const FlowArgs& a, int sm_count, cudaStream_t st);
 bool flow_tc_supported(const rnf_flow* f);
 }  // namespace rnf
 
@@ -157,10 +158,12 @@ static int run_rows(rnf_flow* f, bool inverse, const float* R_in, int64_t N, con
   a.scratch = scratch;
   a.trace = g_trace;
   cudaError_t e;
-  if (mlp_mode == RNF_MLP_TC) {
+  if (mlp_mode != RNF_MLP_FP32) {
     if (!rnf::flow_tc_supported(f)) return fail(RNF_ESTATE, "%s: model was packed without the tensor-core weight image", who);
     a.n_tiles = (N + 127) / 128;
-    e = rnf::launch_flow_tc(a, inverse, f->sm_count, (cudaStream_t)stream);
+    // forward: software-pipelined kernel (flow_tc2.cu); inverse (TMEM-resident bisection) and RNF_MLP_TC_PAIR: flow_tc.cu
+    e = (mlp_mode == RNF_MLP_TC && !inverse) ? rnf::launch_flow_tc2(a, f->sm_count, (cudaStream_t)stream)
+                                             : rnf::launch_flow_tc(a, inverse, f->sm_count, (cudaStream_t)stream);
   } else {
     a.n_tiles = (N + rnf::kV1Threads - 1) / rnf::kV1Threads;
     e = rnf::launch_flow_v1(a, inverse, f->sm_count, (cudaStream_t)stream);
@@ -224,11 +227,12 @@ int rnf_grid_logprob(rnf_flow* f, const float* grid_dev, int64_t G, int64_t g_in
   a.part = part_dev;
   a.trace = g_trace;
   cudaError_t e;
-  if (mlp_mode == RNF_MLP_TC) {
+  if (mlp_mode != RNF_MLP_FP32) {
     if (!rnf::flow_tc_supported(f)) return fail(RNF_ESTATE, "rnf_grid_logprob: model was packed without the tensor-core weight image");
     a.tiles_per_image = (G + 127) / 128;
     a.n_tiles = a.tiles_per_image * B;
-    e = rnf::launch_flow_tc(a, false, f->sm_count, (cudaStream_t)stream);
+    e = mlp_mode == RNF_MLP_TC ? rnf::launch_flow_tc2(a, f->sm_count, (cudaStream_t)stream)
+                               : rnf::launch_flow_tc(a, false, f->sm_count, (cudaStream_t)stream);
   } else {
     a.tiles_per_image = (G + rnf::kV1Threads - 1) / rnf::kV1Threads;
     a.n_tiles = a.tiles_per_image * B;
