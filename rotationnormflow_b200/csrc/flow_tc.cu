@@ -39,6 +39,10 @@ namespace {
 #define TRACE(i) do { } while (0)
 #endif
 
+#ifndef RNF_TC_INTERLEAVE_TILES
+#define RNF_TC_INTERLEAVE_TILES 0      // measured: 2 % slower than contiguous warp groups per tile
+#endif
+
 constexpr int kThreads = 512;
 constexpr int kRows = 128;                        // rows per tile = TMEM lanes
 
@@ -101,10 +105,19 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
   const int warp = tid >> 5, lane = tid & 31;
 
   TileCtx c;
+#if RNF_TC_INTERLEAVE_TILES
+  // warps {0-3, 8-11} = tile 0, {4-7, 12-15} = tile 1: the scheduler prefers high warp ids, so interleaving the tiles'
+  // warp groups keeps either tile from always winning the issue slot
+  c.tile = (warp >> 2) & 1;
+  c.half = warp >> 3;
+  c.row = (warp & 3) * 32 + lane;
+  c.elected = tid == 128 * c.tile;
+#else
   c.tile = warp >> 3;
   c.half = (warp >> 2) & 1;
   c.row = (warp & 3) * 32 + lane;
   c.elected = (tid & 255) == 0;
+#endif
   c.bars = smem_u32(smem + kOffBar);
   c.par_mma0 = c.par_mma1 = c.par_w = 0;
 
@@ -141,8 +154,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
   const int64_t total_steps = my_items * n_mob;     // Mobius layer executions of this CTA
   const uint8_t* wbytes = reinterpret_cast<const uint8_t*>(a.weights);
   // One bulk copy per piece of a layer image; `piece` 0..2 = W1..W3, 3 = W4, 4 = aux (into buffer `abuf`).
-  auto load_piece = [&](int64_t mob_step, int piece, int abuf) {
-    const uint8_t* src = wbytes + s_moff[mob_step % n_mob] * 4;
+  auto load_piece = [&](int mob_idx, int piece, int abuf) {   // mob_idx: index into the Mobius layer table
+    const uint8_t* src = wbytes + s_moff[mob_idx] * 4;
     uint32_t dst, bytes, bar;
     if (piece < 3) { src += piece * kW1Bytes; dst = kOffW + piece * kW1Bytes; bytes = kW1Bytes; bar = BAR_W_FULL + piece; }
     else if (piece == 3) { src += kHidW; dst = kOffLastW; bytes = kLastW; bar = BAR_W_FULL + 3; }
@@ -153,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
   if (tid == 0 && total_steps > 0) {                // prime every region with the first Mobius layer(s)
     for (int piece = 0; piece < 4; ++piece) load_piece(0, piece, 0);
     load_piece(0, 4, 0);
-    if (total_steps > 1) load_piece(1, 4, 1);
+    if (total_steps > 1) load_piece(n_mob > 1 ? 1 : 0, 4, 1);
   }
 
   uint8_t* a_hi = smem + kOffA + c.tile * 32768;
@@ -169,6 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
   const uint32_t tm_stash = c.tmem_d + 64 + 32 * c.half;     // h0 of my 32 hidden columns (free TMEM columns)
   const uint32_t tm_mine = c.tmem_d + 128 * c.half;          // my 128 fc_last columns = 32 mixture components
   int64_t step = 0;                                  // Mobius executions finished by this tile (same on both tiles)
+  int mob_cur = 0;                                   // step % n_mob, maintained without a 64-bit modulo
   // Ping-pong of the two tiles: the MLP chain of one tile (latency bound: four dependent GEMM round trips) is made to run
   // against the mixture arithmetic of the other (issue bound).  Named barrier 5 + t = "tile t may start its chain".
   const int turn_mine = 5 + c.tile, turn_other = 6 - c.tile;
@@ -250,6 +264,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       // fp32 side data of this layer (first-layer columns, biases): double buffered on the layer parity, every thread
       // observes the bulk copy itself
       const int abuf = (int)(step & 1);
+      const int mob_n1 = mob_cur + 1 >= n_mob ? mob_cur + 1 - n_mob : mob_cur + 1;     // (step + 1) % n_mob
+      const int mob_n2 = mob_n1 + 1 >= n_mob ? mob_n1 + 1 - n_mob : mob_n1 + 1;         // (step + 2) % n_mob
       mbar_wait(c.bars + 8 * (BAR_AUX_FULL + abuf), (uint32_t)((step >> 1) & 1));
       const uint8_t* aux = smem + kOffAux + abuf * kAuxStride;
       const float4* sFirst = reinterpret_cast<const float4*>(aux);
@@ -297,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
         tc_fence_after();
         TRACE(5 + 4 * l);
         // W_l is dead once BOTH tiles' GEMM l has completed: the second tile to get here refills it for the next layer
-        if (c.elected && (atomicAdd(&s_cnt[l], 1) & 1) && step + 1 < total_steps) load_piece(step + 1, l, 0);
+        if (c.elected && (atomicAdd(&s_cnt[l], 1) & 1) && step + 1 < total_steps) load_piece(mob_n1, l, 0);
         float acc[32];
         tmem_ld32(c.tmem_d + 32 * c.half, acc);
         const float4* bias4 = reinterpret_cast<const float4*>(sBiasHid + 64 * l + 32 * c.half);
@@ -350,35 +366,42 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       // ---- mixture of my 32 components, 8 at a time straight from TMEM ----
       float S_sp = 0.0f, S_th = 0.0f, S_f = 0.0f;
       const float zr = dot3(x, P.r), zv = dot3(x, P.v);   // in-plane coordinates of the moving column
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        float acc[32];
-        tmem_ld32(tm_mine + 32 * q, acc);
-        const float4* b4 = reinterpret_cast<const float4*>(sBiasLast + 128 * c.half + 32 * q);
+      {
+        // 8 chunks of 16 columns (4 components); the load of chunk i+1 is in flight while chunk i is being evaluated
+        float buf[2][16];
+        tmem_ld16_async(tm_mine, buf[0]);
+        tmem_ld_wait16(buf[0]);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float4 b = b4[k];
-          const float sp = softplus_fast(fmaf(acc[4 * k], kWUnscale, b.x));
-          float al, be, omw;
-          comp_prep2(P, fmaf(acc[4 * k + 1], kWUnscale, b.y), fmaf(acc[4 * k + 2], kWUnscale, b.z),
-                     fmaf(acc[4 * k + 3], kWUnscale, b.w), al, be, omw);
-          S_sp += sp;
-          if (!INV) {
-            float th, f;
-            comp_eval2(zr, zv, al, be, omw, th, f);
-            S_th = fmaf(sp, th, S_th);
-            S_f = fmaf(sp, f, S_f);
-          } else {
-            acc[4 * k] = al; acc[4 * k + 1] = be; acc[4 * k + 2] = omw; acc[4 * k + 3] = sp;
+        for (int i = 0; i < 8; ++i) {
+          float* acc = buf[i & 1];
+          if (i < 7) tmem_ld16_async(tm_mine + 16 * (i + 1), buf[(i + 1) & 1]);
+          const float4* b4 = reinterpret_cast<const float4*>(sBiasLast + 128 * c.half + 16 * i);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 b = b4[k];
+            const float sp = softplus_fast(fmaf(acc[4 * k], kWUnscale, b.x));
+            float al, be, omw;
+            comp_prep2(P, fmaf(acc[4 * k + 1], kWUnscale, b.y), fmaf(acc[4 * k + 2], kWUnscale, b.z),
+                       fmaf(acc[4 * k + 3], kWUnscale, b.w), al, be, omw);
+            S_sp += sp;
+            if (!INV) {
+              float th, f;
+              comp_eval2(zr, zv, al, be, omw, th, f);
+              S_th = fmaf(sp, th, S_th);
+              S_f = fmaf(sp, f, S_f);
+            } else {
+              acc[4 * k] = al; acc[4 * k + 1] = be; acc[4 * k + 2] = omw; acc[4 * k + 3] = sp;
+            }
           }
+          if (INV) tmem_st16(tm_mine + 16 * i, acc);   // prepared parameters stay in my TMEM lane for the bisection
+          if (i < 7) tmem_ld_wait16(buf[(i + 1) & 1]);
         }
-        if (INV) tmem_st32(tm_mine + 32 * q, acc);   // prepared parameters stay in my TMEM lane for the bisection
       }
       TRACE(18);
       // W4 is dead once both chunks of BOTH tiles have completed (the elected thread sits in half 0: check chunk B too)
       if (c.elected) {
         mbar_wait(bar_mma1, c.par_mma1 ^ 1u);
-        if ((atomicAdd(&s_cnt[3], 1) & 1) && step + 1 < total_steps) load_piece(step + 1, 3, 0);
+        if ((atomicAdd(&s_cnt[3], 1) & 1) && step + 1 < total_steps) load_piece(mob_n1, 3, 0);
         c.par_w ^= 0xFu;
       }
       // ---- exchange partial sums between the two halves of the row (fixed summation order) ----
@@ -388,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       // Past this barrier every thread of the tile is done with this layer's aux buffer: when both tiles are, it is
       // refilled with the side data of the layer after next.
       TRACE(19);
-      if (c.elected && (atomicAdd(&s_cnt[4], 1) & 1) && step + 2 < total_steps) load_piece(step + 2, 4, abuf);
+      if (c.elected && (atomicAdd(&s_cnt[4], 1) & 1) && step + 2 < total_steps) load_piece(mob_n2, 4, abuf);
       S_sp = x_lo[0] + x_hi[0];
       float nx[3], nz[3];
       if (!INV) {
@@ -411,15 +434,21 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
           float sn, cs;
           sincosf(x0, &sn, &cs);
           float Fs = 0.0f;
-#pragma unroll 1
-          for (int q = 0; q < 4; ++q) {
-            float prm[32];
-            tmem_ld32(tm_mine + 32 * q, prm);
+          {
+            float buf[2][16];
+            tmem_ld16_async(tm_mine, buf[0]);
+            tmem_ld_wait16(buf[0]);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              float th, f;
-              comp_eval2(cs, sn, prm[4 * k], prm[4 * k + 1], prm[4 * k + 2], th, f);
-              Fs = fmaf(prm[4 * k + 3], th, Fs);
+            for (int i = 0; i < 8; ++i) {
+              const float* prm = buf[i & 1];
+              if (i < 7) tmem_ld16_async(tm_mine + 16 * (i + 1), buf[(i + 1) & 1]);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float th, f;
+                comp_eval2(cs, sn, prm[4 * k], prm[4 * k + 1], prm[4 * k + 2], th, f);
+                Fs = fmaf(prm[4 * k + 3], th, Fs);
+              }
+              if (i < 7) tmem_ld_wait16(buf[(i + 1) & 1]);
             }
           }
           const int slot = (1 + (it & 1)) * 128;     // slots 1 / 2 (slot 0 still holds S_sp of slow readers)
@@ -454,6 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       set_col(R, p2, nz);
       TRACE(20);
       ++step;
+      mob_cur = mob_n1;
     }
 
     // ================================ outputs ================================

@@ -26,7 +26,7 @@ CAFF_FLOATS = 64 + 3 * (64 * 64 + 64) + 16 * 64 + 16
 TC_AVAILABLE = True    # csrc/flow_tc.cu: tcgen05 conditioner (forward, inverse and grid mode)
 TC_WEIGHT_SCALE = 256.0  # fp16 weight planes are stored times 2^8 (kWScale in csrc/flow_tc.cu)
 
-_MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC, "tc_pair": _cabi.RNF_MLP_TC_PAIR}
+_MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC, "tc_pipe": _cabi.RNF_MLP_TC_PIPE}
 
 
 def default_mlp_mode() -> str:
