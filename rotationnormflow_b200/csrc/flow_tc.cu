@@ -43,6 +43,13 @@ namespace {
 #define RNF_TC_INTERLEAVE_TILES 0      // measured: 2 % slower than contiguous warp groups per tile
 #endif
 
+#ifndef RNF_TC_NAP_NS
+#define RNF_TC_NAP_NS 100
+#endif
+#ifndef RNF_TC_YIELD
+#define RNF_TC_YIELD 0      // mixture warps back off while the other tile runs a chain burst (see BUSY below)
+#endif
+
 constexpr int kThreads = 512;
 constexpr int kRows = 128;                        // rows per tile = TMEM lanes
 
@@ -119,11 +126,18 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
   c.elected = (tid & 255) == 0;
 #endif
   c.bars = smem_u32(smem + kOffBar);
+  // warp-uniform (provably: broadcast from lane 0) flag of the warp that issues this tile's MMAs
+  const bool issuer_warp = __shfl_sync(0xffffffffu, (int)c.elected, 0) != 0;
   c.par_mma0 = c.par_mma1 = c.par_w = 0;
 
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kOffMisc);
   int* s_cnt = reinterpret_cast<int*>(smem + kOffMisc + 4);                // consumers done: [0..2] W1..W3, [3] W4, [4] aux
-  long long* s_moff = reinterpret_cast<long long*>(smem + kOffMisc + 32);  // w_off_tc of Mobius layers, execution order
+  long long* s_moff = reinterpret_cast<long long*>(smem + kOffMisc + 32);
+  // Issue-slot arbitration between the tiles.  The hardware scheduler keeps issuing from the (always ready) mixture warps and
+  // starves the other tile's short, latency-critical chain bursts (first layer / epilogues / MMA issue): measured with
+  // tools/tc_timeline.py, a tile made no chain progress at all while the other tile was in its mixture.  The chain tile
+  // therefore raises s_busy[tile] around its bursts and the mixture loop of the other tile naps while it is up.
+  volatile int* s_busy = reinterpret_cast<volatile int*>(smem + kOffMisc + 24);  // w_off_tc of Mobius layers, execution order
 
   // ---- one-time setup -------------------------------------------------------------------------------------------------
   int n_mob = 0;
@@ -137,6 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
   if (tid == 0) {
     for (int i = 0; i < BAR_COUNT; ++i) mbar_init(c.bars + 8 * i, 1);
     for (int i = 0; i < 5; ++i) s_cnt[i] = 0;
+    s_busy[0] = s_busy[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -267,6 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       const int mob_n1 = mob_cur + 1 >= n_mob ? mob_cur + 1 - n_mob : mob_cur + 1;     // (step + 1) % n_mob
       const int mob_n2 = mob_n1 + 1 >= n_mob ? mob_n1 + 1 - n_mob : mob_n1 + 1;         // (step + 2) % n_mob
       mbar_wait(c.bars + 8 * (BAR_AUX_FULL + abuf), (uint32_t)((step >> 1) & 1));
+      if (RNF_TC_YIELD && c.elected) s_busy[c.tile] = 1;
       const uint8_t* aux = smem + kOffAux + abuf * kAuxStride;
       const float4* sFirst = reinterpret_cast<const float4*>(aux);
       const float* sBiasHid = reinterpret_cast<const float*>(aux + 1024);
@@ -300,18 +316,23 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
         named_bar(bar_tile, 256);
         TRACE(3 + 4 * l);
         if (RNF_TC_TURN_RELEASE == l) named_arrive(turn_other, 512);
-        if (c.elected) {
+        if (issuer_warp) {
           mbar_wait(c.bars + 8 * (BAR_W_FULL + l), (c.par_w >> l) & 1u);
           tc_fence_after();
-          const uint32_t wb = w_hid_d + l * (kW1Bytes >> 4);
-          issue_split_gemm(tmem_base + c.tile * 256, a_hi_d, a_lo_d, wb, wb + (8192 >> 4), umma_idesc(128, 64));
-          umma_commit(bar_mma0);
+          if (elect_one_sync()) {
+            const uint32_t wb = w_hid_d + l * (kW1Bytes >> 4);
+            issue_split_gemm(tmem_base + c.tile * 256, a_hi_d, a_lo_d, wb, wb + (8192 >> 4), umma_idesc(128, 64));
+            umma_commit(bar_mma0);
+            if (RNF_TC_YIELD) s_busy[c.tile] = 0;
+          }
+          __syncwarp();
         }
         TRACE(4 + 4 * l);
         mbar_wait(bar_mma0, c.par_mma0);
         c.par_mma0 ^= 1;
         tc_fence_after();
         TRACE(5 + 4 * l);
+        if (RNF_TC_YIELD && c.elected) s_busy[c.tile] = 1;
         // W_l is dead once BOTH tiles' GEMM l has completed: the second tile to get here refills it for the next layer
         if (c.elected && (atomicAdd(&s_cnt[l], 1) & 1) && step + 1 < total_steps) load_piece(mob_n1, l, 0);
         float acc[32];
@@ -347,14 +368,19 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       named_bar(bar_tile, 256);
       TRACE(15);
       if (RNF_TC_TURN_RELEASE == 3) named_arrive(turn_other, 512);
-      if (c.elected) {
+      if (issuer_warp) {
         mbar_wait(c.bars + 8 * (BAR_W_FULL + 3), (c.par_w >> 3) & 1u);
         tc_fence_after();
-        const uint32_t d = tmem_base + c.tile * 256;
-        issue_split_gemm(d, a_hi_d, a_lo_d, w_last_d, w_last_d + (32768 >> 4), umma_idesc(128, 128));
-        umma_commit(bar_mma0);
-        issue_split_gemm(d + 128, a_hi_d, a_lo_d, w_last_d + (16384 >> 4), w_last_d + ((32768 + 16384) >> 4), umma_idesc(128, 128));
-        umma_commit(bar_mma1);
+        if (elect_one_sync()) {
+          const uint32_t d = tmem_base + c.tile * 256;
+          issue_split_gemm(d, a_hi_d, a_lo_d, w_last_d, w_last_d + (32768 >> 4), umma_idesc(128, 128));
+          umma_commit(bar_mma0);
+          issue_split_gemm(d + 128, a_hi_d, a_lo_d, w_last_d + (16384 >> 4), w_last_d + ((32768 + 16384) >> 4), umma_idesc(128, 128));
+          umma_commit(bar_mma1);
+          if (RNF_TC_YIELD) s_busy[c.tile] = 0;
+        }
+        __syncwarp();
+        c.par_w ^= 0xFu;                             // every lane of the issuing warp keeps the weight-phase parities
       }
       TRACE(16);
       if (c.half == 0) { mbar_wait(bar_mma0, c.par_mma0); } else { mbar_wait(bar_mma1, c.par_mma1); }
@@ -375,6 +401,9 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
         for (int i = 0; i < 8; ++i) {
           float* acc = buf[i & 1];
           if (i < 7) tmem_ld16_async(tm_mine + 16 * (i + 1), buf[(i + 1) & 1]);
+          if (RNF_TC_YIELD) {
+            for (int nap = 0; nap < 64 && s_busy[1 - c.tile]; ++nap) __nanosleep(RNF_TC_NAP_NS);
+          }
           const float4* b4 = reinterpret_cast<const float4*>(sBiasLast + 128 * c.half + 16 * i);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -402,7 +431,6 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       if (c.elected) {
         mbar_wait(bar_mma1, c.par_mma1 ^ 1u);
         if ((atomicAdd(&s_cnt[3], 1) & 1) && step + 1 < total_steps) load_piece(mob_n1, 3, 0);
-        c.par_w ^= 0xFu;
       }
       // ---- exchange partial sums between the two halves of the row (fixed summation order) ----
       x_mine[0] = S_sp; x_mine[128] = S_th; x_mine[256] = S_f;

@@ -149,6 +149,22 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float v[16]) {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// elect.sync: exactly one lane of a converged warp returns true.  Issuing tcgen05.mma under this predicate (inside a
+// warp-uniform branch) lets ptxas move the operands to uniform registers with one R2UR each; with an ordinary
+// per-thread condition it emits an ELECT / R2UR.BROADCAST / BRA.U.ANY loop per MMA (~15 instructions, ~85 cycles each).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xFFFFFFFF;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor layout:
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=2 (SW128) [61,64)).
 constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);          // bits [32,64): SBO = 1024 B, version 1, SW128

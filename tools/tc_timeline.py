@@ -28,3 +28,9 @@ for s in range(2, 6):
         row = t[tile, s]
         base = int(row[0])
         print(f"step {40+s} tile {tile}: start @{base - t0:7d} | " + " ".join(f"{names[i]}+{int(row[i]) - int(row[i-1])}" for i in range(1, 21)))
+# absolute phase boundaries: chain = [start, iss4], wait = [iss4, mmaA], mixture = [mmaA, mix], tail = [mix, end]
+print("absolute timeline (cycles since first stamp): chain_start, fc_last_issued, mixture_start, mixture_end, layer_end")
+for s in range(2, 6):
+    for tile in range(2):
+        row = t[tile, s]
+        print(f"step {40+s} tile {tile}: " + " ".join(f"{int(row[i]) - t0:7d}" for i in (0, 16, 17, 18, 20)))
