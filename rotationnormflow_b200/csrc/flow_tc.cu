@@ -46,6 +46,9 @@ namespace {
 #ifndef RNF_TC_NAP_NS
 #define RNF_TC_NAP_NS 100
 #endif
+#ifndef RNF_TC_MIX_YIELD
+#define RNF_TC_MIX_YIELD 0      // nanosleep(0) per 4 mixture components = a scheduler yield: +3 % (measured 0..150 ns: same)
+#endif
 #ifndef RNF_TC_YIELD
 #define RNF_TC_YIELD 0      // mixture warps back off while the other tile runs a chain burst (see BUSY below)
 #endif
@@ -393,18 +396,18 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       float S_sp = 0.0f, S_th = 0.0f, S_f = 0.0f;
       const float zr = dot3(x, P.r), zv = dot3(x, P.v);   // in-plane coordinates of the moving column
       {
-        // 8 chunks of 16 columns (4 components); the load of chunk i+1 is in flight while chunk i is being evaluated
-        float buf[2][16];
-        tmem_ld16_async(tm_mine, buf[0]);
-        tmem_ld_wait16(buf[0]);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float* acc = buf[i & 1];
-          if (i < 7) tmem_ld16_async(tm_mine + 16 * (i + 1), buf[(i + 1) & 1]);
+        // 8 chunks of 16 columns (4 components each); the TMEM load of the next chunk is in flight while the current one is
+        // evaluated (two register buffers).  Rolled into 4 iterations of 2 chunks: the fully unrolled body (32 KB of SASS)
+        // overflowed the instruction cache (ncu: stall_no_instruction 0.53 per issue).
+        float buf0[16], buf1[16];
+        auto eval4 = [&](float* acc, int col) {
           if (RNF_TC_YIELD) {
             for (int nap = 0; nap < 64 && s_busy[1 - c.tile]; ++nap) __nanosleep(RNF_TC_NAP_NS);
           }
-          const float4* b4 = reinterpret_cast<const float4*>(sBiasLast + 128 * c.half + 16 * i);
+#if RNF_TC_MIX_YIELD >= 0
+          __nanosleep(RNF_TC_MIX_YIELD);               // scheduler hint: let the other tile's chain warps in
+#endif
+          const float4* b4 = reinterpret_cast<const float4*>(sBiasLast + 128 * c.half + col);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float4 b = b4[k];
@@ -422,8 +425,18 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
               acc[4 * k] = al; acc[4 * k + 1] = be; acc[4 * k + 2] = omw; acc[4 * k + 3] = sp;
             }
           }
-          if (INV) tmem_st16(tm_mine + 16 * i, acc);   // prepared parameters stay in my TMEM lane for the bisection
-          if (i < 7) tmem_ld_wait16(buf[(i + 1) & 1]);
+          if (INV) tmem_st16(tm_mine + col, acc);      // prepared parameters stay in my TMEM lane for the bisection
+        };
+        tmem_ld16_async(tm_mine, buf0);
+        tmem_ld_wait16(buf0);
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          tmem_ld16_async(tm_mine + 32 * j + 16, buf1);
+          eval4(buf0, 32 * j);
+          tmem_ld_wait16(buf1);
+          if (j < 3) tmem_ld16_async(tm_mine + 32 * j + 32, buf0);
+          eval4(buf1, 32 * j + 16);
+          if (j < 3) tmem_ld_wait16(buf0);
         }
       }
       TRACE(18);
@@ -463,20 +476,25 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
           sincosf(x0, &sn, &cs);
           float Fs = 0.0f;
           {
-            float buf[2][16];
-            tmem_ld16_async(tm_mine, buf[0]);
-            tmem_ld_wait16(buf[0]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float* prm = buf[i & 1];
-              if (i < 7) tmem_ld16_async(tm_mine + 16 * (i + 1), buf[(i + 1) & 1]);
+            float buf0[16], buf1[16];
+            auto probe4 = [&](const float* prm) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 float th, f;
                 comp_eval2(cs, sn, prm[4 * k], prm[4 * k + 1], prm[4 * k + 2], th, f);
                 Fs = fmaf(prm[4 * k + 3], th, Fs);
               }
-              if (i < 7) tmem_ld_wait16(buf[(i + 1) & 1]);
+            };
+            tmem_ld16_async(tm_mine, buf0);
+            tmem_ld_wait16(buf0);
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+              tmem_ld16_async(tm_mine + 32 * j + 16, buf1);
+              probe4(buf0);
+              tmem_ld_wait16(buf1);
+              if (j < 3) tmem_ld16_async(tm_mine + 32 * j + 32, buf0);
+              probe4(buf1);
+              if (j < 3) tmem_ld_wait16(buf0);
             }
           }
           const int slot = (1 + (it & 1)) * 128;     // slots 1 / 2 (slot 0 still holds S_sp of slow readers)
