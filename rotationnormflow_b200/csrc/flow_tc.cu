@@ -74,7 +74,7 @@ static_assert(kOffA % 1024 == 0 && kOffLastW % 1024 == 0, "UMMA SW128 tiles need
 // mbarrier slots
 enum { BAR_W_FULL = 0 /* W1,W2,W3,W4 */, BAR_AUX_FULL = 4 /* [2] */, BAR_MMA = 6 /* [tile][2] */, BAR_COUNT = 10 };
 
-// Split 32 non-negative fp32 activations (columns 32h .. 32h+31 of row r) into fp16 hi / lo and store them into the
+// ReLU + split 32 fp32 pre-activations (columns 32h .. 32h+31 of row r) into fp16 hi / lo and store them into the
 // K-major SW128 A operand: element (r, k) lives at (r/8)*1024 + (r%8)*128 + ((k/8) ^ (r%8))*16 + (k%8)*2.
 __device__ __forceinline__ void store_a_operand(uint8_t* a_hi, uint8_t* a_lo, int r, int h, const float v[32]) {
   const int rbase = (r >> 3) * 1024 + (r & 7) * 128;
@@ -83,12 +83,7 @@ __device__ __forceinline__ void store_a_operand(uint8_t* a_hi, uint8_t* a_lo, in
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float x0 = v[8 * c + 2 * e], x1 = v[8 * c + 2 * e + 1];
-      const __half2 hh = __floats2half2_rn(x0, x1);
-      const float2 back = __half22float2(hh);
-      const __half2 ll = __floats2half2_rn(x0 - back.x, x1 - back.y);
-      hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
-      lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+      relu_split2(v[8 * c + 2 * e], v[8 * c + 2 * e + 1], hi[e], lo[e]);     // ReLU is applied here
     }
     const int off = rbase + (((4 * h + c) ^ (r & 7)) << 4);
     *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -304,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
             const float4 f = sFirst[32 * c.half + 4 * j4 + e];
             const float hv = fmaf(f.z, y[2], fmaf(f.y, y[1], fmaf(f.x, y[0], f.w))) + cc[e];
             h0[4 * j4 + e] = hv;
-            act[4 * j4 + e] = fmaxf(hv, 0.0f);
+            act[4 * j4 + e] = hv;                    // ReLU happens inside the fp16 split
           }
         }
         store_a_operand(a_hi, a_lo, c.row, c.half, act);
@@ -345,10 +340,10 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 b = bias4[j4];
-            acc[4 * j4 + 0] = fmaxf(fmaf(acc[4 * j4 + 0], kWUnscale, b.x), 0.0f);
-            acc[4 * j4 + 1] = fmaxf(fmaf(acc[4 * j4 + 1], kWUnscale, b.y), 0.0f);
-            acc[4 * j4 + 2] = fmaxf(fmaf(acc[4 * j4 + 2], kWUnscale, b.z), 0.0f);
-            acc[4 * j4 + 3] = fmaxf(fmaf(acc[4 * j4 + 3], kWUnscale, b.w), 0.0f);
+            acc[4 * j4 + 0] = fmaf(acc[4 * j4 + 0], kWUnscale, b.x);
+            acc[4 * j4 + 1] = fmaf(acc[4 * j4 + 1], kWUnscale, b.y);
+            acc[4 * j4 + 2] = fmaf(acc[4 * j4 + 2], kWUnscale, b.z);
+            acc[4 * j4 + 3] = fmaf(acc[4 * j4 + 3], kWUnscale, b.w);
           }
         } else {                                     // relu_last(x0 + x)   (flow/condition.py:29)
           float h0[32];
@@ -356,10 +351,10 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 b = bias4[j4];
-            acc[4 * j4 + 0] = fmaxf(fmaf(acc[4 * j4 + 0], kWUnscale, b.x) + h0[4 * j4 + 0], 0.0f);
-            acc[4 * j4 + 1] = fmaxf(fmaf(acc[4 * j4 + 1], kWUnscale, b.y) + h0[4 * j4 + 1], 0.0f);
-            acc[4 * j4 + 2] = fmaxf(fmaf(acc[4 * j4 + 2], kWUnscale, b.z) + h0[4 * j4 + 2], 0.0f);
-            acc[4 * j4 + 3] = fmaxf(fmaf(acc[4 * j4 + 3], kWUnscale, b.w) + h0[4 * j4 + 3], 0.0f);
+            acc[4 * j4 + 0] = fmaf(acc[4 * j4 + 0], kWUnscale, b.x) + h0[4 * j4 + 0];
+            acc[4 * j4 + 1] = fmaf(acc[4 * j4 + 1], kWUnscale, b.y) + h0[4 * j4 + 1];
+            acc[4 * j4 + 2] = fmaf(acc[4 * j4 + 2], kWUnscale, b.z) + h0[4 * j4 + 2];
+            acc[4 * j4 + 3] = fmaf(acc[4 * j4 + 3], kWUnscale, b.w) + h0[4 * j4 + 3];
           }
         }
         store_a_operand(a_hi, a_lo, c.row, c.half, acc);

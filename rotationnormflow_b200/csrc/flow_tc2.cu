@@ -52,7 +52,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// 16 non-negative activations (hidden units 16cg .. 16cg+15 of row r) -> fp16 hi / lo planes of the K-major SW128 A operand
+// ReLU + split of 16 pre-activations (hidden units 16cg .. 16cg+15 of row r) -> fp16 hi / lo planes of the K-major SW128 A operand
 __device__ __forceinline__ void store_a16(uint8_t* a_hi, uint8_t* a_lo, int r, int cg, const float v[16]) {
   const int rbase = (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
@@ -60,12 +60,7 @@ __device__ __forceinline__ void store_a16(uint8_t* a_hi, uint8_t* a_lo, int r, i
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float x0 = v[8 * c + 2 * e], x1 = v[8 * c + 2 * e + 1];
-      const __half2 hh = __floats2half2_rn(x0, x1);
-      const float2 back = __half22float2(hh);
-      const __half2 ll = __floats2half2_rn(x0 - back.x, x1 - back.y);
-      hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
-      lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+      relu_split2(v[8 * c + 2 * e], v[8 * c + 2 * e + 1], hi[e], lo[e]);     // ReLU is applied here
     }
     const int off = rbase + (((2 * cg + c) ^ (r & 7)) << 4);
     *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -318,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc2_kernel(const FlowArgs a)
           const float4 f = sFirst[16 * cg + 4 * j4 + e];
           const float hv = fmaf(f.z, y[2], fmaf(f.y, y[1], fmaf(f.x, y[0], f.w))) + cc[e];
           h0[4 * j4 + e] = hv;
-          act[4 * j4 + e] = fmaxf(hv, 0.0f);
+          act[4 * j4 + e] = hv;
         }
       }
       tmem_st16(tm_lane + 256 * t + 64 + 16 * cg, h0);
@@ -335,10 +330,10 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc2_kernel(const FlowArgs a)
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const float4 b = bias4[j4];
-          act[4 * j4 + 0] = fmaxf(fmaf(act[4 * j4 + 0], kWUnscale, b.x), 0.0f);
-          act[4 * j4 + 1] = fmaxf(fmaf(act[4 * j4 + 1], kWUnscale, b.y), 0.0f);
-          act[4 * j4 + 2] = fmaxf(fmaf(act[4 * j4 + 2], kWUnscale, b.z), 0.0f);
-          act[4 * j4 + 3] = fmaxf(fmaf(act[4 * j4 + 3], kWUnscale, b.w), 0.0f);
+          act[4 * j4 + 0] = fmaf(act[4 * j4 + 0], kWUnscale, b.x);
+          act[4 * j4 + 1] = fmaf(act[4 * j4 + 1], kWUnscale, b.y);
+          act[4 * j4 + 2] = fmaf(act[4 * j4 + 2], kWUnscale, b.z);
+          act[4 * j4 + 3] = fmaf(act[4 * j4 + 3], kWUnscale, b.w);
         }
       } else {                                       // relu_last(x0 + x)   (flow/condition.py:29)
         float h0[16];
@@ -346,10 +341,10 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc2_kernel(const FlowArgs a)
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const float4 b = bias4[j4];
-          act[4 * j4 + 0] = fmaxf(fmaf(act[4 * j4 + 0], kWUnscale, b.x) + h0[4 * j4 + 0], 0.0f);
-          act[4 * j4 + 1] = fmaxf(fmaf(act[4 * j4 + 1], kWUnscale, b.y) + h0[4 * j4 + 1], 0.0f);
-          act[4 * j4 + 2] = fmaxf(fmaf(act[4 * j4 + 2], kWUnscale, b.z) + h0[4 * j4 + 2], 0.0f);
-          act[4 * j4 + 3] = fmaxf(fmaf(act[4 * j4 + 3], kWUnscale, b.w) + h0[4 * j4 + 3], 0.0f);
+          act[4 * j4 + 0] = fmaf(act[4 * j4 + 0], kWUnscale, b.x) + h0[4 * j4 + 0];
+          act[4 * j4 + 1] = fmaf(act[4 * j4 + 1], kWUnscale, b.y) + h0[4 * j4 + 1];
+          act[4 * j4 + 2] = fmaf(act[4 * j4 + 2], kWUnscale, b.z) + h0[4 * j4 + 2];
+          act[4 * j4 + 3] = fmaf(act[4 * j4 + 3], kWUnscale, b.w) + h0[4 * j4 + 3];
         }
       }
     }

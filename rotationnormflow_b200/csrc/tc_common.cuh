@@ -165,6 +165,18 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// ReLU + error-compensated fp16 split of two activations in four instructions:
+//   hi = cvt.rz.relu.satfinite(t)          (round toward zero: the residual of a non-negative t is non-negative)
+//   lo = cvt.rn.relu.satfinite(t - hi)     (t < 0: hi = 0, residual = t < 0 -> 0)
+// so the ReLU of flow/condition.py:14-20 costs nothing, at one bit of the 22-bit split (hi 11 bits by truncation + lo 11).
+// Returns packed half2 words {x0 in the low half, x1 in the high half}; satfinite keeps huge activations finite
+// (fp16 range: |activation| < 65504, twice that through hi + lo).
+__device__ __forceinline__ void relu_split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - back.y), "f"(x0 - back.x));
+}
+
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor layout:
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=2 (SW128) [61,64)).
 constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);          // bits [32,64): SBO = 1024 B, version 1, SW128
