@@ -42,8 +42,6 @@ extern "C" {
 /* kernel selection for the conditioner MLP (flow/condition.py:24-30) */
 #define RNF_MLP_FP32 0    /* FP32 CUDA-core FMA: the exact-precision path                             */
 #define RNF_MLP_TC 1      /* tcgen05 tensor cores, error-compensated split operands, FP32 accumulate  */
-#define RNF_MLP_TC_PIPE 2 /* same arithmetic, half-step software-pipelined schedule (csrc/flow_tc2.cu, forward only;
-                             measured slower than RNF_MLP_TC: kept for A/B runs)              */
 
 /*
  * One entry per layer, in module order (index i == `layers.{i}` of the reference state dict).

@@ -60,16 +60,18 @@ constexpr int kRows = 128;                        // rows per tile = TMEM lanes
 //      [W1 | W2 | W3 : each (hi 64x64, lo 64x64) fp16 SW128][W4 : hi 256x64, lo 256x64][aux : first[64][4], b1..b3, b4' fp32]
 //      and every piece is brought in by its own bulk copy as soon as its previous contents are dead. ----
 constexpr int kOffW = 0;
-constexpr int kOffLastW = kHidW;                  // 49152
-constexpr int kOffAux = kOffLastW + kLastW;       // 114688, double buffered (layer parity)
-constexpr int kOffA = kOffAux + 2 * kAuxStride;   // 120832 = 118 * 1024 : [tile][hi|lo] 128x64 fp16 (16 KB each)
-constexpr int kOffXchg = kOffA + 4 * 16384;       // [tile][half][3][128] fp32
+constexpr int kOffLastW = kHidW;                  // 55296
+constexpr int kOffAux = kOffLastW + kLastW;       // 129024, double buffered (layer parity)
+constexpr int kOffA = kOffAux + 2 * kAuxStride;   // 131072 = 128 * 1024 : [tile][hi|lo] 128x64 fp16 (16 KB each)
+constexpr int kOffOnes = kOffA + 4 * 16384;       // constant [128 x 16] fp16 tile, ones in K columns 0 and 1 (no swizzle)
+constexpr int kOffXchg = kOffOnes + 4096;         // [tile][half][3][128] fp32
 constexpr int kOffRed = kOffXchg + 2 * 2 * 3 * 128 * 4;   // [tile] reduction scratch
 constexpr int kOffBar = kOffRed + 2 * 128;
 constexpr int kOffMisc = kOffBar + 8 * 16;        // tmem base, counters, Mobius offset table
 constexpr int kSmemBytes = kOffMisc + 32 + 64 * 8;
 constexpr int kSmemAlloc = kSmemBytes + 1024;     // slack for manual 1024 B alignment
-static_assert(kOffA % 1024 == 0 && kOffLastW % 1024 == 0, "UMMA SW128 tiles need 1024 B alignment");
+static_assert(kOffA % 1024 == 0 && kOffLastW % 1024 == 0 && kW1Bytes % 1024 == 0, "UMMA SW128 tiles need 1024 B alignment");
+static_assert(kSmemAlloc <= 232448, "exceeds the 227 KB shared-memory limit of an sm_100 CTA");
 
 // mbarrier slots
 enum { BAR_W_FULL = 0 /* W1,W2,W3,W4 */, BAR_AUX_FULL = 4 /* [2] */, BAR_MMA = 6 /* [tile][2] */, BAR_COUNT = 10 };
@@ -152,6 +154,10 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
     s_busy[0] = s_busy[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // constant ones tile (bias MMA): row r holds 1.0 in K columns 0 and 1, zero elsewhere
+  // (no-swizzle layout: per 8-row group 128 B for K 0..7 then 128 B for K 8..15; thread tid writes bytes 8 tid .. 8 tid + 7)
+  reinterpret_cast<uint2*>(smem + kOffOnes)[tid] = make_uint2(((tid & 1) == 0 && (tid & 31) < 16) ? 0x3C003C00u : 0u, 0u);
+  fence_proxy_async();
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -186,6 +192,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
   uint8_t* a_lo = a_hi + 16384;
   const uint32_t a_hi_d = umma_desc_lo(smem_u32(a_hi)), a_lo_d = umma_desc_lo(smem_u32(a_lo));
   const uint32_t w_hid_d = umma_desc_lo(smem_u32(smem + kOffW)), w_last_d = umma_desc_lo(smem_u32(smem + kOffLastW));
+  const uint32_t ones_d = umma_desc_lo_ns(smem_u32(smem + kOffOnes));
+  const uint32_t bias_hid_d = umma_desc_lo_ns(smem_u32(smem + kOffW + 16384)), bias_last_d = umma_desc_lo_ns(smem_u32(smem + kOffLastW + 65536));
   float* xchg = reinterpret_cast<float*>(smem + kOffXchg) + c.tile * (2 * 3 * 128);   // [half][slot 0..2][row]
   float* x_mine = xchg + c.half * 384 + c.row;
   const float* x_lo = xchg + c.row;
@@ -283,8 +291,6 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
       if (RNF_TC_YIELD && c.elected) s_busy[c.tile] = 1;
       const uint8_t* aux = smem + kOffAux + abuf * kAuxStride;
       const float4* sFirst = reinterpret_cast<const float4*>(aux);
-      const float* sBiasHid = reinterpret_cast<const float*>(aux + 1024);
-      const float* sBiasLast = reinterpret_cast<const float*>(aux + 1792);
 
       // ---- first conditioner layer for my 32 columns; pre-activation stashed in TMEM for the residual ----
       {
@@ -319,7 +325,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
           tc_fence_after();
           if (elect_one_sync()) {
             const uint32_t wb = w_hid_d + l * (kW1Bytes >> 4);
-            issue_split_gemm(tmem_base + c.tile * 256, a_hi_d, a_lo_d, wb, wb + (8192 >> 4), umma_idesc(128, 64));
+            issue_split_gemm(tmem_base + c.tile * 256, a_hi_d, a_lo_d, wb, wb + (8192 >> 4), ones_d, bias_hid_d + l * (kW1Bytes >> 4),
+                             umma_idesc(128, 64));
             umma_commit(bar_mma0);
             if (RNF_TC_YIELD) s_busy[c.tile] = 0;
           }
@@ -335,27 +342,11 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
         if (c.elected && (atomicAdd(&s_cnt[l], 1) & 1) && step + 1 < total_steps) load_piece(mob_n1, l, 0);
         float acc[32];
         tmem_ld32(c.tmem_d + 32 * c.half, acc);
-        const float4* bias4 = reinterpret_cast<const float4*>(sBiasHid + 64 * l + 32 * c.half);
-        if (l < 2) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = bias4[j4];
-            acc[4 * j4 + 0] = fmaf(acc[4 * j4 + 0], kWUnscale, b.x);
-            acc[4 * j4 + 1] = fmaf(acc[4 * j4 + 1], kWUnscale, b.y);
-            acc[4 * j4 + 2] = fmaf(acc[4 * j4 + 2], kWUnscale, b.z);
-            acc[4 * j4 + 3] = fmaf(acc[4 * j4 + 3], kWUnscale, b.w);
-          }
-        } else {                                     // relu_last(x0 + x)   (flow/condition.py:29)
+        if (l == 2) {                                // relu_last(x0 + x)   (flow/condition.py:29); biases come out of the GEMM
           float h0[32];
           tmem_ld32(tm_stash, h0);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = bias4[j4];
-            acc[4 * j4 + 0] = fmaf(acc[4 * j4 + 0], kWUnscale, b.x) + h0[4 * j4 + 0];
-            acc[4 * j4 + 1] = fmaf(acc[4 * j4 + 1], kWUnscale, b.y) + h0[4 * j4 + 1];
-            acc[4 * j4 + 2] = fmaf(acc[4 * j4 + 2], kWUnscale, b.z) + h0[4 * j4 + 2];
-            acc[4 * j4 + 3] = fmaf(acc[4 * j4 + 3], kWUnscale, b.w) + h0[4 * j4 + 3];
-          }
+          for (int j = 0; j < 32; ++j) acc[j] += h0[j];
         }
         store_a_operand(a_hi, a_lo, c.row, c.half, acc);
         TRACE(6 + 4 * l);
@@ -371,9 +362,10 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t d = tmem_base + c.tile * 256;
-          issue_split_gemm(d, a_hi_d, a_lo_d, w_last_d, w_last_d + (32768 >> 4), umma_idesc(128, 128));
+          issue_split_gemm(d, a_hi_d, a_lo_d, w_last_d, w_last_d + (32768 >> 4), ones_d, bias_last_d, umma_idesc(128, 128));
           umma_commit(bar_mma0);
-          issue_split_gemm(d + 128, a_hi_d, a_lo_d, w_last_d + (16384 >> 4), w_last_d + ((32768 + 16384) >> 4), umma_idesc(128, 128));
+          issue_split_gemm(d + 128, a_hi_d, a_lo_d, w_last_d + (16384 >> 4), w_last_d + ((32768 + 16384) >> 4), ones_d,
+                           bias_last_d + (4096 >> 4), umma_idesc(128, 128));
           umma_commit(bar_mma1);
           if (RNF_TC_YIELD) s_busy[c.tile] = 0;
         }
@@ -395,25 +387,22 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
         // evaluated (two register buffers).  Rolled into 4 iterations of 2 chunks: the fully unrolled body (32 KB of SASS)
         // overflowed the instruction cache (ncu: stall_no_instruction 0.53 per issue).
         float buf0[16], buf1[16];
-        auto eval4 = [&](float* acc, int col) {
+        auto eval4 = [&](float* acc, int col) {      // col: first of the 16 fc_last columns (of my half) in `acc`
           if (RNF_TC_YIELD) {
             for (int nap = 0; nap < 64 && s_busy[1 - c.tile]; ++nap) __nanosleep(RNF_TC_NAP_NS);
           }
 #if RNF_TC_MIX_YIELD >= 0
           __nanosleep(RNF_TC_MIX_YIELD);               // scheduler hint: let the other tile's chain warps in
 #endif
-          const float4* b4 = reinterpret_cast<const float4*>(sBiasLast + 128 * c.half + col);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float4 b = b4[k];
-            const float sp = softplus_fast(fmaf(acc[4 * k], kWUnscale, b.x));
+            const float sp = softplus_fast(acc[4 * k]);
             float al, be, omw;
-            comp_prep2(P, fmaf(acc[4 * k + 1], kWUnscale, b.y), fmaf(acc[4 * k + 2], kWUnscale, b.z),
-                       fmaf(acc[4 * k + 3], kWUnscale, b.w), al, be, omw);
+            comp_prep2(P, acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3], al, be, omw);
             S_sp += sp;
             if (!INV) {
               float th, f;
-              comp_eval2(zr, zv, al, be, omw, th, f);
+              comp_eval2_fwd(zr, zv, al, be, omw, th, f);
               S_th = fmaf(sp, th, S_th);
               S_f = fmaf(sp, f, S_f);
             } else {

@@ -71,6 +71,29 @@ __device__ __forceinline__ float atan2_wrapped_fast(float y, float x) {
   return y < 0.0f ? kTwoPi - p : p;
 }
 
+// Forward direction only: the evaluation point is the moving column itself, z = -|x| r, and |w| < 0.7 by construction
+// (flow/mobiusflow.py:72), so h_w(z) stays within +-2 asin(0.7) of the angle pi: x < 0 always and the
+// wrapped angle is pi - atan(y / |x|).  One select fewer than the full-circle version.
+__device__ __forceinline__ float atan2_left_half_plane(float y, float x) {
+  const float ay = fabsf(y), ax = fabsf(x);
+  const float mx = fmaxf(ay, ax), mn = fminf(ay, ax);
+  const float q = mn * rcp_approx(mx);
+  const float s = q * q;
+  float p = -0.0024470302741974592f;
+  p = fmaf(p, s, 0.013750280253589153f);
+  p = fmaf(p, s, -0.03627016767859459f);
+  p = fmaf(p, s, 0.06284360587596893f);
+  p = fmaf(p, s, -0.08673170208930969f);
+  p = fmaf(p, s, 0.11037994176149368f);
+  p = fmaf(p, s, -0.14279110729694366f);
+  p = fmaf(p, s, 0.1999976634979248f);
+  p = fmaf(p, s, -0.3333333134651184f);
+  p = p * s;
+  p = fmaf(p, q, q);                                  // atan(q), q in [0,1]
+  p = ay > ax ? 1.5707963267948966f - p : p;          // atan(|y| / |x|)
+  return y < 0.0f ? kPi + p : kPi - p;
+}
+
 // Per-layer constants of a row: frame (r, v).
 struct Plane {
   float r[3], v[3];
@@ -102,6 +125,15 @@ __device__ __forceinline__ void comp_eval2(float zr, float zv, float al, float b
   f = omw * rcp_approx(dd);
   const float hr = fmaf(f, dr, -al), hv = fmaf(f, dv, -be);
   theta = atan2_wrapped_fast(hv, hr);
+}
+
+// forward-direction variant of comp_eval2 (evaluation point = the moving column: h always in the left half plane)
+__device__ __forceinline__ void comp_eval2_fwd(float zr, float zv, float al, float be, float omw, float& theta, float& f) {
+  const float dr = zr - al, dv = zv - be;
+  const float dd = fmaf(dv, dv, dr * dr);
+  f = omw * rcp_approx(dd);
+  const float hr = fmaf(f, dr, -al), hv = fmaf(f, dv, -be);
+  theta = atan2_left_half_plane(hv, hr);
 }
 
 __device__ __forceinline__ float comp_f2(float zr, float zv, float al, float be, float omw) {

@@ -12,16 +12,20 @@
 
 namespace rnf {
 
-constexpr float kWUnscale = 1.0f / 256.0f;        // host scales the fp16 weight planes by 2^8
-
-// Packed global image of one Mobius conditioner (== the shared-memory pieces):
-//   [W1 | W2 | W3 : each (hi 64x64, lo 64x64) fp16 SW128][W4 : hi 256x64, lo 256x64][aux : first[64][4], b1..b3, b4' fp32]
-constexpr int kW1Bytes = 2 * 8192;                // one hidden layer: hi | lo planes
-constexpr int kHidW = 3 * kW1Bytes;               // 49152
-constexpr int kLastW = 2 * 32768;                 // [hi|lo] 256x64 fp16
-constexpr int kAuxBytes = 1024 + 768 + 1024;      // first[64][4] ; b1,b2,b3 ; permuted fc_last bias   (fp32)
-constexpr int kAuxStride = 3072;
-static_assert(kHidW + kLastW + kAuxBytes == kMobFloats * 4, "TC image has the same size as the FP32 image");
+// Packed global image of one Mobius conditioner (== the shared-memory pieces, one bulk copy each):
+//   W1 | W2 | W3 : each [hi 64x64 | lo 64x64] fp16 K-major SWIZZLE_128B, then the bias block [64 x 16] fp16 (no swizzle)
+//   W4           : [hi 256x64 | lo 256x64] fp16 SW128 (outputs permuted: component c owns columns 4c..4c+3), bias block [256 x 16]
+//   aux          : first[64][4] fp32  (W0[:, :3] and b0 of fc_first)
+// A bias block holds (b_hi, b_lo) in its K columns 0 and 1; multiplied by a constant [128 x 16] tile with ones in those two
+// columns it initialises the accumulator with the bias, so the CUDA cores never touch a bias or a scale factor.
+constexpr int kBiasBlkHid = 64 * 32;
+constexpr int kBiasBlkLast = 256 * 32;
+constexpr int kW1Bytes = 2 * 8192 + kBiasBlkHid;  // 18432
+constexpr int kHidW = 3 * kW1Bytes;               // 55296
+constexpr int kLastW = 2 * 32768 + kBiasBlkLast;  // 73728
+constexpr int kAuxBytes = 1024;
+constexpr int kAuxStride = 1024;
+constexpr int kTcImageBytes = kHidW + kLastW + kAuxBytes;   // 130048
 
 // ------------------------------------------------ PTX wrappers ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -181,18 +185,23 @@ __device__ __forceinline__ void relu_split2(float x0, float x1, uint32_t& hi, ui
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=2 (SW128) [61,64)).
 constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);          // bits [32,64): SBO = 1024 B, version 1, SW128
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+// No-swizzle K-major ("interleave") descriptor for the 16-wide bias / ones blocks: 8 x 16 B core matrices, the two K halves
+// 128 B apart (LBO), 8-row groups 256 B apart (SBO): element (r, k) at (r/8)*256 + (k/8)*128 + (r%8)*16 + (k%8)*2.
+constexpr uint32_t kDescHiNS = 16u | (1u << 14);
+__device__ __forceinline__ uint32_t umma_desc_lo_ns(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (8u << 16); }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=b=F16 (0), K-major both, N>>3 [17,23), M>>4 [24,29)
 __device__ __host__ constexpr uint32_t umma_idesc(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// Issue D[128 x N] = A[128 x 64] . W[N x 64]^T with the 3-product split.  a_* / b_* are the descriptor low words of the
-// hi / lo fp16 planes (each K-major SW128, 128 B per row); a K step of 16 elements = 32 B = +2 in the address field.
-// Small terms are accumulated first.
+// Issue D[128 x N] = bias + A[128 x 64] . W[N x 64]^T: one K = 16 MMA of the constant ones tile against the bias block
+// initialises the accumulator, then the 3-product split  Alo.Whi + Ahi.Wlo + Ahi.Whi  accumulates on top.  a_* / b_* are
+// descriptor low words (hi / lo fp16 planes, K-major SW128, 128 B per row); a K step of 16 elements = 32 B = +2.
 __device__ __forceinline__ void issue_split_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                                 uint32_t idesc) {
+                                                 uint32_t ones_ns, uint32_t bias_ns, uint32_t idesc) {
+  umma_f16(d_tmem, ones_ns, bias_ns, kDescHiNS, idesc, 0);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, kDescHi, idesc, k > 0);
+  for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, kDescHi, idesc, 1);
 #pragma unroll
   for (int k = 0; k < 4; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, kDescHi, idesc, 1);
 #pragma unroll

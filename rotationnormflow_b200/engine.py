@@ -24,9 +24,10 @@ AFF_INV = 20
 CAFF_FLOATS = 64 + 3 * (64 * 64 + 64) + 16 * 64 + 16
 
 TC_AVAILABLE = True    # csrc/flow_tc.cu: tcgen05 conditioner (forward, inverse and grid mode)
-TC_WEIGHT_SCALE = 256.0  # fp16 weight planes are stored times 2^8 (kWScale in csrc/flow_tc.cu)
+TC_WEIGHT_SCALE = 1.0    # fp16 hi/lo weight planes are stored unscaled (biases ride along as a K=16 block, see pack_mobius_tc)
+MOB_TC_FLOATS = (3 * (2 * 8192 + 64 * 32) + (2 * 32768 + 256 * 32) + 1024) // 4   # kTcImageBytes / 4 in csrc/tc_common.cuh
 
-_MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC, "tc_pipe": _cabi.RNF_MLP_TC_PIPE}
+_MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC}
 
 
 def default_mlp_mode() -> str:
@@ -91,24 +92,37 @@ def _split_fp16(W: np.ndarray):
     return hi, lo
 
 
+def _bias_block(b: np.ndarray) -> np.ndarray:
+    """[N] fp32 bias -> [N x 16] fp16 block in the no-swizzle K-major UMMA layout, (b_hi, b_lo) in K columns 0 and 1:
+    element (n, k) at (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2 bytes.  Against the kernel's constant ones tile it yields b."""
+    N = b.shape[0]
+    hi = b.astype(np.float16)
+    lo = (b - hi.astype(np.float32)).astype(np.float16)
+    out = np.zeros(N * 16, dtype=np.float16)
+    n = np.arange(N)
+    base = ((n // 8) * 256 + (n % 8) * 16) // 2
+    out[base] = hi
+    out[base + 1] = lo
+    return out
+
+
 def pack_mobius_tc(cond_sd: dict) -> np.ndarray:
-    """Tensor-core image of one Mobius conditioner = the exact shared-memory image of csrc/flow_tc.cu:
-    [3 x (hi 64x64, lo 64x64) fp16 SW128 | (hi 256x64, lo 256x64) fp16 SW128 | first[64][4], b1,b2,b3, b4' fp32]
-    returned as float32 words (MOB_FLOATS of them)."""
+    """Tensor-core image of one Mobius conditioner = the exact shared-memory pieces of csrc/flow_tc.cu:
+    3 x [hi 64x64 | lo 64x64 fp16 SW128 | bias block 64x16] | [hi 256x64 | lo 256x64 SW128 | bias block 256x16] | first[64][4] fp32
+    returned as float32 words (MOB_TC_FLOATS of them)."""
     W0, b0 = _np(cond_sd["fc_first.weight"]), _np(cond_sd["fc_first.bias"])
     parts = []
     for j in (1, 3, 5):
         hi, lo = _split_fp16(_np(cond_sd[f"layers.{j}.weight"]))          # nn.Linear weight is [out=N, in=K]: K-major
-        parts += [_umma_k_major_sw128(hi).view(np.float32), _umma_k_major_sw128(lo).view(np.float32)]
+        parts += [_umma_k_major_sw128(hi).view(np.float32), _umma_k_major_sw128(lo).view(np.float32),
+                  _bias_block(_np(cond_sd[f"layers.{j}.bias"])).view(np.float32)]
     perm = _last_layer_perm(K_SEGMENTS)
     hi, lo = _split_fp16(_np(cond_sd["fc_last.weight"])[perm])
-    parts += [_umma_k_major_sw128(hi).view(np.float32), _umma_k_major_sw128(lo).view(np.float32)]
+    parts += [_umma_k_major_sw128(hi).view(np.float32), _umma_k_major_sw128(lo).view(np.float32),
+              _bias_block(_np(cond_sd["fc_last.bias"])[perm]).view(np.float32)]
     parts.append(np.concatenate([W0[:, :3], b0[:, None]], axis=1).astype(np.float32).reshape(-1))
-    for j in (1, 3, 5):
-        parts.append(_np(cond_sd[f"layers.{j}.bias"]))
-    parts.append(_np(cond_sd["fc_last.bias"])[perm])
     blk = np.concatenate(parts).astype(np.float32, copy=False)
-    assert blk.size == MOB_FLOATS
+    assert blk.size == MOB_TC_FLOATS
     return blk
 
 

@@ -10,10 +10,30 @@ from conftest import ROOT
 def _coeffs():
     """Coefficients c0..c8 (ascending powers of s = q^2) read back from the Horner evaluation in the header."""
     src = open(os.path.join(ROOT, "rotationnormflow_b200", "csrc", "mobius_fast.cuh")).read()
-    body = src[src.index("atan2_wrapped_fast"):src.index("struct Plane")]
+    body = src[src.index("float atan2_wrapped_fast"):src.index("atan2_left_half_plane")]
     first = re.search(r"float p = (-?[0-9.e-]+)f;", body).group(1)
     rest = re.findall(r"p = fmaf\(p, s, (-?[0-9.e-]+)f\);", body)
     return ([float(first)] + [float(v) for v in rest])[::-1]
+
+
+def test_both_atan_variants_share_the_polynomial():
+    src = open(os.path.join(ROOT, "rotationnormflow_b200", "csrc", "mobius_fast.cuh")).read()
+    a = src[src.index("float atan2_wrapped_fast"):src.index("atan2_left_half_plane")]
+    b = src[src.index("float atan2_left_half_plane"):src.index("struct Plane")]
+    pat = r"fmaf\(p, s, (-?[0-9.e-]+)f\)"
+    assert re.findall(pat, a) == re.findall(pat, b) and len(re.findall(pat, a)) == 8
+
+
+def test_left_half_plane_identity():
+    """x < 0:  atan2(y, x) wrapped to [0, 2 pi)  ==  pi - atan(y / |x|)  (the forward-direction shortcut)."""
+    rng = np.random.default_rng(1)
+    y, x = rng.standard_normal(100000), -np.abs(rng.standard_normal(100000)) - 1e-3
+    ref = np.arctan2(y, x)
+    ref = np.where(ref >= 0, ref, ref + 2 * np.pi)
+    p = np.arctan(np.minimum(np.abs(y), -x) / np.maximum(np.abs(y), -x))
+    p = np.where(np.abs(y) > -x, np.pi / 2 - p, p)
+    got = np.where(y < 0, np.pi + p, np.pi - p)
+    assert np.abs(got - ref).max() < 1e-12
 
 
 def _fma32(a, b, c):
