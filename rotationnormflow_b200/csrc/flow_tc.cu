@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
 #endif
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float sp = softplus_fast(acc[4 * k]);
+            const float sp = softplus_log2(acc[4 * k]);   // weights in units of ln 2: only ratios of sums are used
             float al, be, omw;
             comp_prep2(P, acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3], al, be, omw);
             S_sp += sp;

@@ -39,15 +39,22 @@ __device__ __forceinline__ float lg2_approx(float x) {
   return r;
 }
 
-// softplus(a) = log(1 + e^a), identity above 20 (torch threshold).  For e^a < 2^-7 the series e(1 - e/2 + e^2/3 - e^3/4)
-// keeps the relative accuracy that 1 + e would lose.
-__device__ __forceinline__ float softplus_fast(float a) {
-  const float e = ex2_approx(a * 1.4426950408889634f);
-  const float big = 0.6931471805599453f * lg2_approx(1.0f + e);
-  const float small = e * fmaf(e, fmaf(e, fmaf(e, -0.25f, 0.3333333333f), -0.5f), 1.0f);
+// Mixture weight of a component, in units of ln 2:  softplus(a) / ln 2 = log2(1 + 2^t),  t = a log2(e).
+// theta' = sum_k sp_k theta_k / sum_k sp_k and log sum_k sp_k f_k / sum_k sp_k are ratios, so the common factor ln 2
+// never has to be applied.  torch's softplus is the identity above a = 20 (threshold), i.e. t above 20 log2(e); for
+// 2^t < 2^-7 the series e (1 - e/2) / ln 2 replaces log2(1 + e), whose argument would round away e (absolute error of the
+// weight <= 2e-7 either way: what matters is the error relative to the sum of the 64 weights).
+__device__ __forceinline__ float softplus_log2(float a) {
+  const float t = a * 1.4426950408889634f;
+  const float e = ex2_approx(t);
+  const float big = lg2_approx(1.0f + e);
+  const float small = e * fmaf(e, -0.7213475204444817f, 1.4426950408889634f);
   const float sp = e < 0.0078125f ? small : big;
-  return a > 20.0f ? a : sp;
+  return t > 28.853900817779268f ? t : sp;
 }
+
+// softplus(a) = log(1 + e^a) itself (same construction, natural units).
+__device__ __forceinline__ float softplus_fast(float a) { return 0.6931471805599453f * softplus_log2(a); }
 
 // atan2(y, x) wrapped to [0, 2 pi)  == torch.where(t >= 0, t, t + 2 pi) of flow/mobiusflow.py:94-99.
 __device__ __forceinline__ float atan2_wrapped_fast(float y, float x) {

@@ -69,6 +69,12 @@ def test_octant_reduction_covers_the_circle():
 
 
 def test_softplus_series_branch():
-    e = np.float64(0.0078125)
-    series = e * (1 - e / 2 + e * e / 3 - e ** 3 / 4)
-    assert abs(series - np.log1p(e)) / np.log1p(e) < 1e-9
+    """e (1 - e/2) against log1p(e) below the 2^-7 switch-over: relative error <= e^2/3, absolute <= 2e-7."""
+    e = np.linspace(0, 0.0078125, 1001)[1:]
+    series = e * (1 - e / 2)
+    assert (np.abs(series - np.log1p(e)) / np.log1p(e)).max() < 2.1e-5
+    assert np.abs(series - np.log1p(e)).max() < 2e-7
+    # constants in the header are the series coefficients divided by ln 2
+    src = open(os.path.join(ROOT, "rotationnormflow_b200", "csrc", "mobius_fast.cuh")).read()
+    m = re.search(r"small = e \* fmaf\(e, (-?[0-9.]+)f, ([0-9.]+)f\)", src)
+    assert abs(float(m.group(2)) - 1 / np.log(2)) < 1e-12 and abs(float(m.group(1)) + 0.5 / np.log(2)) < 1e-12
