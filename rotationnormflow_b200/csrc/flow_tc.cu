@@ -394,21 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
 #if RNF_TC_MIX_YIELD >= 0
           __nanosleep(RNF_TC_MIX_YIELD);               // scheduler hint: let the other tile's chain warps in
 #endif
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float sp = softplus_log2(acc[4 * k]);   // weights in units of ln 2: only ratios of sums are used
-            float al, be, omw;
-            comp_prep2(P, acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3], al, be, omw);
-            S_sp += sp;
-            if (!INV) {
-              float th, f;
-              comp_eval2_fwd(zr, zv, al, be, omw, th, f);
-              S_th = fmaf(sp, th, S_th);
-              S_f = fmaf(sp, f, S_f);
-            } else {
-              acc[4 * k] = al; acc[4 * k + 1] = be; acc[4 * k + 2] = omw; acc[4 * k + 3] = sp;
-            }
-          }
+          mixture4<!INV>(P, zr, zv, acc, S_sp, S_th, S_f);
           if (INV) tmem_st16(tm_mine + col, acc);      // prepared parameters stay in my TMEM lane for the bisection
         };
         tmem_ld16_async(tm_mine, buf0);

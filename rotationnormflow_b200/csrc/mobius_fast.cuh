@@ -148,4 +148,85 @@ __device__ __forceinline__ float comp_f2(float zr, float zv, float al, float be,
   return omw * rcp_approx(fmaf(dv, dv, dr * dr));
 }
 
+
+// Four mixture components at once, written stage by stage (structure-of-arrays) so that the four independent dependency
+// chains (~200 cycles deep each: EX2 -> LG2, SQRT -> RCP -> RCP -> RCP -> 9-term Horner) are issued interleaved; ptxas keeps
+// the component-by-component order of a plain loop and leaves a warp with an ILP of ~1.5.
+// raw[16] = (logit, w.x, w.y, w.z) x 4 as they come out of the fc_last GEMM.  FWD: accumulates the three mixture sums.
+// !FWD: overwrites raw with the prepared parameters (alpha', beta', 1 - |w'|^2, weight) for the bisection.
+template <bool FWD>
+__device__ __forceinline__ void mixture4(const Plane& P, float zr, float zv, float raw[16], float& S_sp, float& S_th, float& S_f) {
+  float sp[4], al[4], be[4], omw[4];
+  {
+    float t[4], e[4], a[4], b[4], n2[4], rt[4], s[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { t[k] = raw[4 * k] * 1.4426950408889634f; e[k] = ex2_approx(t[k]); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      a[k] = fmaf(raw[4 * k + 3], P.r[2], fmaf(raw[4 * k + 2], P.r[1], raw[4 * k + 1] * P.r[0]));
+      b[k] = fmaf(raw[4 * k + 3], P.v[2], fmaf(raw[4 * k + 2], P.v[1], raw[4 * k + 1] * P.v[0]));
+      n2[k] = fmaf(b[k], b[k], a[k] * a[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rt[k] = sqrt_approx(n2[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float big = lg2_approx(1.0f + e[k]);
+      const float small = e[k] * fmaf(e[k], -0.7213475204444817f, 1.4426950408889634f);
+      const float v = e[k] < 0.0078125f ? small : big;
+      sp[k] = t[k] > 28.853900817779268f ? t[k] : v;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] = 0.7f * rcp_approx(1.0f + rt[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      al[k] = s[k] * a[k];
+      be[k] = s[k] * b[k];
+      omw[k] = fmaf(-be[k], be[k], fmaf(-al[k], al[k], 1.0f));
+    }
+  }
+  if (FWD) {
+    float f[4], hr[4], hv[4], q[4], p[4], ay[4], ax[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float dr = zr - al[k], dv = zv - be[k];
+      f[k] = omw[k] * rcp_approx(fmaf(dv, dv, dr * dr));
+      hr[k] = fmaf(f[k], dr, -al[k]);
+      hv[k] = fmaf(f[k], dv, -be[k]);
+      ay[k] = fabsf(hv[k]);
+      ax[k] = fabsf(hr[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = fminf(ay[k], ax[k]) * rcp_approx(fmaxf(ay[k], ax[k]));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) p[k] = -0.0024470302741974592f;
+    // Horner over the four components in lock step (same coefficients as atan2_wrapped_fast)
+#define RNF_HORNER(cf) _Pragma("unroll") for (int k = 0; k < 4; ++k) p[k] = fmaf(p[k], q[k] * q[k], cf)
+    RNF_HORNER(0.013750280253589153f);
+    RNF_HORNER(-0.03627016767859459f);
+    RNF_HORNER(0.06284360587596893f);
+    RNF_HORNER(-0.08673170208930969f);
+    RNF_HORNER(0.11037994176149368f);
+    RNF_HORNER(-0.14279110729694366f);
+    RNF_HORNER(0.1999976634979248f);
+    RNF_HORNER(-0.3333333134651184f);
+#undef RNF_HORNER
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float at = fmaf(p[k] * (q[k] * q[k]), q[k], q[k]);          // atan(q), q in [0,1]
+      at = ay[k] > ax[k] ? 1.5707963267948966f - at : at;          // atan(|hv| / |hr|); hr < 0 always in the forward direction
+      const float th = hv[k] < 0.0f ? kPi + at : kPi - at;
+      S_sp += sp[k];
+      S_th = fmaf(sp[k], th, S_th);
+      S_f = fmaf(sp[k], f[k], S_f);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      S_sp += sp[k];
+      raw[4 * k] = al[k]; raw[4 * k + 1] = be[k]; raw[4 * k + 2] = omw[k]; raw[4 * k + 3] = sp[k];
+    }
+  }
+}
+
 }  // namespace rnf
