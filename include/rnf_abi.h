@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RNF_ABI_VERSION 3
+#define RNF_ABI_VERSION 4
 
 /* error codes */
 #define RNF_OK 0
@@ -146,6 +146,14 @@ int rnf_grid_logprob(rnf_flow* flow, const float* grid_dev, int64_t G, int64_t g
  * (72*8^level rotations, index = tilt*npix + pixel, RING pixel order), float64 math -> float32.
  */
 int rnf_healpix_grid(int level, int64_t begin, int64_t end, float* R_out_dev, void* stream);
+
+/*
+ * MatrixFisherN._log_prob (utils/fisher.py:217-232) for image-major rows: R_dev [N,3,3] with N = B * rows_per_image,
+ * A9_dev [B,9], c_dev [B] = sum of proper singular values + log normaliser (rotationnormflow_b200.fisher.fisher_constants)
+ *   out[i] = sum(A_b * R_i) - c_b
+ */
+int rnf_fisher_log_prob(const float* A9_dev, const float* c_dev, int64_t B, const float* R_dev, int64_t N, float* out_dev,
+                        void* stream);
 
 #ifdef __cplusplus
 }

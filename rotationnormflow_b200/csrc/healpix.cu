@@ -74,7 +74,29 @@ __global__ void healpix_grid_kernel(int level, int64_t begin, int64_t end, float
   }
 }
 
+// MatrixFisherN._log_prob (utils/fisher.py:217-232): out[i] = sum(A_b * R_i) - c_b, b = image of row i (image-major rows,
+// `rows_per_image` rotations each, as inputs.reshape(B, -1, 3, 3) does).  HBM bound: 36 B in + 4 B out per rotation.
+__global__ void fisher_logprob_kernel(const float* __restrict__ A9, const float* __restrict__ c, const float* __restrict__ R,
+                                      int64_t N, int64_t rows_per_image, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / rows_per_image;
+    float tr = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) tr = fmaf(__ldg(A9 + b * 9 + k), __ldg(R + i * 9 + k), tr);
+    out[i] = tr - __ldg(c + b);
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_fisher_logprob(const float* A9, const float* c, const float* R, int64_t N, int64_t rows_per_image, float* out,
+                                  cudaStream_t st) {
+  if (N <= 0) return cudaSuccess;
+  int64_t blocks = (N + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fisher_logprob_kernel<<<(unsigned)blocks, 256, 0, st>>>(A9, c, R, N, rows_per_image, out);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_healpix(int level, int64_t begin, int64_t end, float* out, cudaStream_t st) {
   const int64_t n = end - begin;

@@ -251,4 +251,15 @@ int rnf_healpix_grid(int level, int64_t begin, int64_t end, float* R_out_dev, vo
   return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_healpix_grid");
 }
 
+int rnf_fisher_log_prob(const float* A9_dev, const float* c_dev, int64_t B, const float* R_dev, int64_t N, float* out_dev,
+                        void* stream) {
+  if (B <= 0 || N < 0) return fail(RNF_EINVAL, "rnf_fisher_log_prob: bad sizes");
+  if (N == 0) return RNF_OK;
+  if (N % B != 0) return fail(RNF_EINVAL, "rnf_fisher_log_prob: N=%lld rotations do not split evenly over B=%lld images "
+                              "(utils/fisher.py:223 reshapes to (B, -1, 3, 3))", (long long)N, (long long)B);
+  if (!A9_dev || !c_dev || !R_dev || !out_dev) return fail(RNF_EINVAL, "rnf_fisher_log_prob: null buffer");
+  cudaError_t e = rnf::launch_fisher_logprob(A9_dev, c_dev, R_dev, N, N / B, out_dev, (cudaStream_t)stream);
+  return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_fisher_log_prob");
+}
+
 }  // extern "C"

@@ -23,3 +23,38 @@ def fisher_constants(A: torch.Tensor):
     log_norm = -0.5 * torch.log(8 * math.pi * (S0 + S1) * (S2 + S1) * (S0 + S2))
     c = (S0 + S1 + S2) + log_norm
     return A.reshape(-1, 9).contiguous(), c.contiguous()
+
+
+class MatrixFisherN(torch.nn.Module):
+    """Drop-in for the log-prob side of utils/fisher.py:209-232 (``MatrixFisherN(A)._log_prob(inputs)``), type-1 normaliser.
+
+    ``inputs`` [B*Q,3,3] (or anything reshapable to (B,-1,3,3), image-major) on the device of ``A``; returns [B*Q].
+    ``_sample`` (host RNG rejection sampling, utils/fisher.py:117-207) is outside the hot-path scope."""
+
+    def __init__(self, A, norm_type=1, approx_num=None):
+        super().__init__()
+        if norm_type != 1:
+            raise NotImplementedError("only the type-1 (high concentration) normaliser is on the hot path (utils/fisher.py:87-91)")
+        self.A = A
+        self._A9, self._c = fisher_constants(A)
+
+    def _log_prob(self, inputs, context=9):
+        import ctypes as C
+        from . import _cabi
+        lib = _cabi.load()
+        if not inputs.is_cuda:
+            raise RuntimeError("rotationnormflow_b200 runs on a B200 only: `inputs` must be a CUDA tensor (there is no CPU fallback)")
+        if inputs.shape[-1] != 3 or inputs.shape[-2] != 3:
+            raise NotImplementedError("quaternion inputs: convert with quaternion_to_matrix first (utils/fisher.py:219-220)")
+        dev = inputs.device
+        if self._A9.device != dev:
+            self._A9, self._c = self._A9.to(dev), self._c.to(dev)
+        R = inputs.reshape(-1, 3, 3).to(torch.float32).contiguous()
+        out = torch.empty((R.shape[0],), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _cabi.check(lib.rnf_fisher_log_prob(C.c_void_p(self._A9.data_ptr()), C.c_void_p(self._c.data_ptr()), self._A9.shape[0],
+                                                C.c_void_p(R.data_ptr()), R.shape[0], C.c_void_p(out.data_ptr()), st))
+        return out
+
+    log_prob = _log_prob

@@ -263,6 +263,53 @@ def test_grid_log_prob(tag, mode):
     assert (lme_k.double() - olme).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize("tag", ["s_modelnet", "modelnet"])
+def test_matrix_fisher_log_prob(tag):
+    """MatrixFisherN._log_prob against the reference's own output (golden) and the oracle."""
+    from rotationnormflow_b200.fisher import MatrixFisherN
+    g = golden(tag)
+    A = torch.from_numpy(g.z["fisher_A"])
+    base = g.out("fwd", "R", "f32")
+    lp = MatrixFisherN(A.cuda())._log_prob(base.cuda()).cpu()
+    ref = torch.from_numpy(g.z["fisher_logp_f32"])
+    assert ((lp - ref).abs() / ref.abs().clamp(min=1)).max().item() < 1e-5
+    lp64 = orc.fisher_log_prob(A.double(), base.double())
+    assert rel(lp.double(), lp64) < 1e-5
+    with pytest.raises(Exception):
+        MatrixFisherN(A.cuda())._log_prob(base[:5].cuda())      # 5 rows do not split over 4 images
+
+
+def test_eval_call_sites():
+    """estimate_rotation_grid / estimate_rotation_sampling (eval.py:437-462, agent.py:238-266) against the oracle."""
+    from rotationnormflow_b200 import evalpath
+    g = golden("s_symsol")
+    m = _product(g)
+    o = orc.OracleFlow(g.cfg, g.state_dict(), torch.float64)
+    feat = g.feat.cuda()
+    B = feat.shape[0]
+    # grid: level 2 (4608 rotations)
+    off = orc.random_rotations(1, torch.Generator().manual_seed(3))[0]
+    est, out = evalpath.estimate_rotation_grid(m, feat, 4000, offset=off.cuda())
+    grid = orc.healpix_grid(2).double() @ off.double()
+    for b in range(B):
+        _, l64 = o.forward(grid, g.feat[b:b + 1].double().expand(grid.shape[0], -1))
+        k = int(out["argmax"][b])
+        assert float(l64.max() - l64[k]) < 1e-5                       # the chosen grid point is the oracle's maximum (up to fp32 ties)
+        assert (est[b].cpu().double() - grid[k]).abs().max() < 1e-6
+    # sampling: 300 base rotations shared by all images
+    base = orc.random_rotations(300, torch.Generator().manual_seed(4))
+    est, samples, logp = evalpath.estimate_rotation_sampling(m, feat, 300, base_samples=base.cuda())
+    assert samples.shape == (B, 300, 3, 3) and logp.shape == (B, 300)
+    for b in range(B):
+        Ri, li = o.inverse(base.double(), g.feat[b:b + 1].double().expand(300, -1))
+        ref = -li
+        close = (logp[b].cpu().double() - ref).abs() < 5e-3                 # bisection flips move a few samples by ~1e-4 rad
+        assert close.float().mean() > 0.97
+        k = int(logp[b].argmax())
+        assert float(ref.max() - ref[k]) < 5e-3
+        assert (est[b] - samples[b, k]).abs().max() == 0
+
+
 def test_two_rank_grid_sharding_on_one_gpu():
     """Grid sharded in two slices + merge_partials == the unsharded fused reduction (same device, no process group)."""
     from rotationnormflow_b200 import dist as rdist
