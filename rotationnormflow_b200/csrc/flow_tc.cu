@@ -447,23 +447,15 @@ __global__ void __launch_bounds__(kThreads, 1) flow_tc_kernel(const FlowArgs a) 
           float Fs = 0.0f;
           {
             float buf0[16], buf1[16];
-            auto probe4 = [&](const float* prm) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                float th, f;
-                comp_eval2(cs, sn, prm[4 * k], prm[4 * k + 1], prm[4 * k + 2], th, f);
-                Fs = fmaf(prm[4 * k + 3], th, Fs);
-              }
-            };
             tmem_ld16_async(tm_mine, buf0);
             tmem_ld_wait16(buf0);
 #pragma unroll 1
             for (int j = 0; j < 4; ++j) {
               tmem_ld16_async(tm_mine + 32 * j + 16, buf1);
-              probe4(buf0);
+              probe4(cs, sn, buf0, Fs);
               tmem_ld_wait16(buf1);
               if (j < 3) tmem_ld16_async(tm_mine + 32 * j + 32, buf0);
-              probe4(buf1);
+              probe4(cs, sn, buf1, Fs);
               if (j < 3) tmem_ld_wait16(buf0);
             }
           }

@@ -229,4 +229,43 @@ __device__ __forceinline__ void mixture4(const Plane& P, float zr, float zv, flo
   }
 }
 
+// Bisection probe of four prepared components at the in-plane point (zr, zv) = (cos t, sin t): stage-wise like mixture4.
+// prm[16] = (alpha', beta', 1 - |w'|^2, weight) x 4; accumulates sum_k weight_k theta_k(z).  Full-circle atan2: during the
+// bisection z sweeps [pi/2, 3pi/2] and h may land anywhere (flow/mobiusflow.py:226-245).
+__device__ __forceinline__ void probe4(float zr, float zv, const float prm[16], float& Fs) {
+  float hr[4], hv[4], ay[4], ax[4], q[4], p[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float al = prm[4 * k], be = prm[4 * k + 1];
+    const float dr = zr - al, dv = zv - be;
+    const float f = prm[4 * k + 2] * rcp_approx(fmaf(dv, dv, dr * dr));
+    hr[k] = fmaf(f, dr, -al);
+    hv[k] = fmaf(f, dv, -be);
+    ay[k] = fabsf(hv[k]);
+    ax[k] = fabsf(hr[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q[k] = fminf(ay[k], ax[k]) * rcp_approx(fmaxf(ay[k], ax[k]));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) p[k] = -0.0024470302741974592f;
+#define RNF_HORNER(cf) _Pragma("unroll") for (int k = 0; k < 4; ++k) p[k] = fmaf(p[k], q[k] * q[k], cf)
+  RNF_HORNER(0.013750280253589153f);
+  RNF_HORNER(-0.03627016767859459f);
+  RNF_HORNER(0.06284360587596893f);
+  RNF_HORNER(-0.08673170208930969f);
+  RNF_HORNER(0.11037994176149368f);
+  RNF_HORNER(-0.14279110729694366f);
+  RNF_HORNER(0.1999976634979248f);
+  RNF_HORNER(-0.3333333134651184f);
+#undef RNF_HORNER
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float at = fmaf(p[k] * (q[k] * q[k]), q[k], q[k]);
+    at = ay[k] > ax[k] ? 1.5707963267948966f - at : at;
+    at = hr[k] < 0.0f ? kPi - at : at;
+    const float th = hv[k] < 0.0f ? kTwoPi - at : at;
+    Fs = fmaf(prm[4 * k + 3], th, Fs);
+  }
+}
+
 }  // namespace rnf
