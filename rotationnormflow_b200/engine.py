@@ -31,7 +31,8 @@ _MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC}
 
 
 def default_mlp_mode() -> str:
-    return os.environ.get("RNF_MLP_MODE", "fp32")
+    """"tc" (tcgen05 conditioner, the product path) unless RNF_MLP_MODE=fp32 selects the exact-FP32 CUDA-core kernels."""
+    return os.environ.get("RNF_MLP_MODE", "tc")
 
 
 def _np(t: torch.Tensor) -> np.ndarray:
