@@ -155,6 +155,12 @@ int rnf_healpix_grid(int level, int64_t begin, int64_t end, float* R_out_dev, vo
 int rnf_fisher_log_prob(const float* A9_dev, const float* c_dev, int64_t B, const float* R_dev, int64_t N, float* out_dev,
                         void* stream);
 
+/*
+ * min_geodesic_distance_rotmats (utils/utils.py:231-235; K = 1: geodesic_distance_rotmats, :225-228): est_dev [B,3,3],
+ * gt_dev [B,K,3,3] -> out_dev [B] = angle (radians) to the closest ground-truth rotation.  Post-path metric.
+ */
+int rnf_min_geodesic(const float* est_dev, const float* gt_dev, int64_t B, int64_t K, float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -403,6 +403,12 @@ def grid_reduce(logp: torch.Tensor):
     return idx, mx, lme.to(logp.dtype)
 
 
+def min_geodesic_distance_rotmats(r1s: torch.Tensor, r2s: torch.Tensor) -> torch.Tensor:
+    """utils/utils.py:231-235: r1s [n,3,3], r2s [n,k,3,3] -> angle to the closest rotation of each set."""
+    prod = torch.einsum("nij,nkij->nk", r1s, r2s)
+    return torch.acos(torch.clip((prod.max(-1).values - 1.0) / 2.0, -1.0, 1.0))
+
+
 def random_rotations(n: int, generator: torch.Generator | None = None, dtype=torch.float32) -> torch.Tensor:
     """Haar-uniform rotations from normalised Gaussian quaternions (public pytorch3d definition)."""
     o = torch.randn((n, 4), generator=generator, dtype=torch.float64)

@@ -70,6 +70,7 @@ _SIGNATURES = {
     "rnf_grid_logprob": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "rnf_healpix_grid": (C.c_int, [C.c_int, _I64, _I64, _P, _P]),
     "rnf_fisher_log_prob": (C.c_int, [_P, _P, _I64, _P, _I64, _P, _P]),
+    "rnf_min_geodesic": (C.c_int, [_P, _P, _I64, _I64, _P, _P]),
 }
 
 _lib = None

@@ -87,7 +87,33 @@ __global__ void fisher_logprob_kernel(const float* __restrict__ A9, const float*
   }
 }
 
+// min_geodesic_distance_rotmats (utils/utils.py:231-235): angle between est[b] and the closest of its K ground-truth rotations:
+// acos(clip((max_k sum_ij est_ij gt_kij - 1)/2, -1, 1)).  K = 1 is geodesic_distance_rotmats (utils/utils.py:225-228).
+__global__ void min_geodesic_kernel(const float* __restrict__ est, const float* __restrict__ gt, int64_t B, int64_t K,
+                                    float* __restrict__ out) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float e[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) e[i] = __ldg(est + b * 9 + i);
+  float best = -INFINITY;
+  for (int64_t k = 0; k < K; ++k) {
+    const float* g = gt + (b * K + k) * 9;
+    float tr = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) tr = fmaf(e[i], __ldg(g + i), tr);
+    best = fmaxf(best, tr);
+  }
+  out[b] = acosf(fminf(fmaxf((best - 1.0f) * 0.5f, -1.0f), 1.0f));
+}
+
 }  // namespace
+
+cudaError_t launch_min_geodesic(const float* est, const float* gt, int64_t B, int64_t K, float* out, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  min_geodesic_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(est, gt, B, K, out);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_fisher_logprob(const float* A9, const float* c, const float* R, int64_t N, int64_t rows_per_image, float* out,
                                   cudaStream_t st) {

@@ -262,4 +262,12 @@ int rnf_fisher_log_prob(const float* A9_dev, const float* c_dev, int64_t B, cons
   return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_fisher_log_prob");
 }
 
+int rnf_min_geodesic(const float* est_dev, const float* gt_dev, int64_t B, int64_t K, float* out_dev, void* stream) {
+  if (B < 0 || K <= 0) return fail(RNF_EINVAL, "rnf_min_geodesic: bad sizes");
+  if (B == 0) return RNF_OK;
+  if (!est_dev || !gt_dev || !out_dev) return fail(RNF_EINVAL, "rnf_min_geodesic: null buffer");
+  cudaError_t e = rnf::launch_min_geodesic(est_dev, gt_dev, B, K, out_dev, (cudaStream_t)stream);
+  return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_min_geodesic");
+}
+
 }  // extern "C"

@@ -86,6 +86,7 @@ cudaError_t launch_grid_combine(const float* part, int64_t tiles_per_image, int6
                                 int64_t* argmax_out, float* sumexp_out, cudaStream_t st);
 cudaError_t launch_condition(const rnf_flow* f, const float* feat, int64_t B, float* cond, cudaStream_t st);
 cudaError_t launch_healpix(int level, int64_t begin, int64_t end, float* out, cudaStream_t st);
+cudaError_t launch_min_geodesic(const float* est, const float* gt, int64_t B, int64_t K, float* out, cudaStream_t st);
 cudaError_t launch_fisher_logprob(const float* A9, const float* c, const float* R, int64_t N, int64_t rows_per_image, float* out,
                                   cudaStream_t st);
 constexpr int kV1Threads = 256;

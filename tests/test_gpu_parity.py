@@ -310,6 +310,20 @@ def test_eval_call_sites():
         assert (est[b] - samples[b, k]).abs().max() == 0
 
 
+def test_geodesic_metrics():
+    from rotationnormflow_b200 import metrics
+    gen = torch.Generator().manual_seed(9)
+    est = orc.random_rotations(300, gen)
+    gt = orc.random_rotations(300 * 7, gen).reshape(300, 7, 3, 3)
+    gt[:10, 3] = est[:10]                                   # exact hits -> angle 0 (clip protects acos)
+    got = metrics.min_geodesic_distance_rotmats(est.cuda(), gt.cuda()).cpu()
+    ref = orc.min_geodesic_distance_rotmats(est.double(), gt.double())
+    assert (got[10:].double() - ref[10:]).abs().max() < 2e-6 and got[:10].abs().max() < 1e-3
+    single = metrics.geodesic_distance_rotmats(est.cuda(), gt[:, 0].cuda()).cpu()
+    assert (single.double() - orc.min_geodesic_distance_rotmats(est.double(), gt[:, :1].double())).abs().max() < 2e-6
+    assert float(metrics.acc(torch.rad2deg(got), 30.0)) == float((torch.rad2deg(got) <= 30.0).float().mean())
+
+
 def test_two_rank_grid_sharding_on_one_gpu():
     """Grid sharded in two slices + merge_partials == the unsharded fused reduction (same device, no process group)."""
     from rotationnormflow_b200 import dist as rdist

@@ -159,3 +159,17 @@ def test_oracle_against_live_reference():
         Rr, lr = rl.run_reference(m, R, feat, inverse=inv)
         Ro, lo = (o.inverse if inv else o.forward)(R, feat)
         assert (Rr - Ro).abs().max() < 1e-9 and (lr - lo).abs().max() < 1e-9
+
+
+def test_geodesic_metric_against_live_reference():
+    import sys
+    from oracle import ref_loader as rl
+    if not rl.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    if rl.REF_ROOT not in sys.path:
+        sys.path.insert(0, rl.REF_ROOT)
+    import utils.utils as ru                              # std-lib + torch imports only
+    gen = torch.Generator().manual_seed(4)
+    est = orc.random_rotations(50, gen, torch.float64)
+    gt = orc.random_rotations(50 * 5, gen, torch.float64).reshape(50, 5, 3, 3)
+    assert torch.equal(orc.min_geodesic_distance_rotmats(est, gt), ru.min_geodesic_distance_rotmats(est, gt))
