@@ -42,6 +42,7 @@ extern "C" {
 /* kernel selection for the conditioner MLP (flow/condition.py:24-30) */
 #define RNF_MLP_FP32 0    /* FP32 CUDA-core FMA: the exact-precision path                             */
 #define RNF_MLP_TC 1      /* tcgen05 tensor cores, error-compensated split operands, FP32 accumulate  */
+#define RNF_MLP_TC_ROW 2  /* same arithmetic, one thread per rotation (csrc/flow_row.cu)                */
 
 /*
  * One entry per layer, in module order (index i == `layers.{i}` of the reference state dict).

@@ -17,6 +17,7 @@ RNF_LAYER_MOBIUS = 0
 RNF_LAYER_AFFINE = 1
 RNF_MLP_FP32 = 0
 RNF_MLP_TC = 1
+RNF_MLP_TC_ROW = 2
 
 
 class LayerDesc(C.Structure):

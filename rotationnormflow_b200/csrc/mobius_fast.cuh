@@ -154,41 +154,41 @@ __device__ __forceinline__ float comp_f2(float zr, float zv, float al, float be,
 // the component-by-component order of a plain loop and leaves a warp with an ILP of ~1.5.
 // raw[16] = (logit, w.x, w.y, w.z) x 4 as they come out of the fc_last GEMM.  FWD: accumulates the three mixture sums.
 // !FWD: overwrites raw with the prepared parameters (alpha', beta', 1 - |w'|^2, weight) for the bisection.
-template <bool FWD>
-__device__ __forceinline__ void mixture4(const Plane& P, float zr, float zv, float raw[16], float& S_sp, float& S_th, float& S_f) {
-  float sp[4], al[4], be[4], omw[4];
+template <int N, bool FWD>
+__device__ __forceinline__ void mixtureN(const Plane& P, float zr, float zv, float* raw, float& S_sp, float& S_th, float& S_f) {
+  float sp[N], al[N], be[N], omw[N];
   {
-    float t[4], e[4], a[4], b[4], n2[4], rt[4], s[4];
+    float t[N], e[N], a[N], b[N], n2[N], rt[N], s[N];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { t[k] = raw[4 * k] * 1.4426950408889634f; e[k] = ex2_approx(t[k]); }
+    for (int k = 0; k < N; ++k) { t[k] = raw[4 * k] * 1.4426950408889634f; e[k] = ex2_approx(t[k]); }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < N; ++k) {
       a[k] = fmaf(raw[4 * k + 3], P.r[2], fmaf(raw[4 * k + 2], P.r[1], raw[4 * k + 1] * P.r[0]));
       b[k] = fmaf(raw[4 * k + 3], P.v[2], fmaf(raw[4 * k + 2], P.v[1], raw[4 * k + 1] * P.v[0]));
       n2[k] = fmaf(b[k], b[k], a[k] * a[k]);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) rt[k] = sqrt_approx(n2[k]);
+    for (int k = 0; k < N; ++k) rt[k] = sqrt_approx(n2[k]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < N; ++k) {
       const float big = lg2_approx(1.0f + e[k]);
       const float small = e[k] * fmaf(e[k], -0.7213475204444817f, 1.4426950408889634f);
       const float v = e[k] < 0.0078125f ? small : big;
       sp[k] = t[k] > 28.853900817779268f ? t[k] : v;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) s[k] = 0.7f * rcp_approx(1.0f + rt[k]);
+    for (int k = 0; k < N; ++k) s[k] = 0.7f * rcp_approx(1.0f + rt[k]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < N; ++k) {
       al[k] = s[k] * a[k];
       be[k] = s[k] * b[k];
       omw[k] = fmaf(-be[k], be[k], fmaf(-al[k], al[k], 1.0f));
     }
   }
   if (FWD) {
-    float f[4], hr[4], hv[4], q[4], p[4], ay[4], ax[4];
+    float f[N], hr[N], hv[N], q[N], p[N], ay[N], ax[N];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < N; ++k) {
       const float dr = zr - al[k], dv = zv - be[k];
       f[k] = omw[k] * rcp_approx(fmaf(dv, dv, dr * dr));
       hr[k] = fmaf(f[k], dr, -al[k]);
@@ -197,11 +197,11 @@ __device__ __forceinline__ void mixture4(const Plane& P, float zr, float zv, flo
       ax[k] = fabsf(hr[k]);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) q[k] = fminf(ay[k], ax[k]) * rcp_approx(fmaxf(ay[k], ax[k]));
+    for (int k = 0; k < N; ++k) q[k] = fminf(ay[k], ax[k]) * rcp_approx(fmaxf(ay[k], ax[k]));
 #pragma unroll
-    for (int k = 0; k < 4; ++k) p[k] = -0.0024470302741974592f;
+    for (int k = 0; k < N; ++k) p[k] = -0.0024470302741974592f;
     // Horner over the four components in lock step (same coefficients as atan2_wrapped_fast)
-#define RNF_HORNER(cf) _Pragma("unroll") for (int k = 0; k < 4; ++k) p[k] = fmaf(p[k], q[k] * q[k], cf)
+#define RNF_HORNER(cf) _Pragma("unroll") for (int k = 0; k < N; ++k) p[k] = fmaf(p[k], q[k] * q[k], cf)
     RNF_HORNER(0.013750280253589153f);
     RNF_HORNER(-0.03627016767859459f);
     RNF_HORNER(0.06284360587596893f);
@@ -212,7 +212,7 @@ __device__ __forceinline__ void mixture4(const Plane& P, float zr, float zv, flo
     RNF_HORNER(-0.3333333134651184f);
 #undef RNF_HORNER
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < N; ++k) {
       float at = fmaf(p[k] * (q[k] * q[k]), q[k], q[k]);          // atan(q), q in [0,1]
       at = ay[k] > ax[k] ? 1.5707963267948966f - at : at;          // atan(|hv| / |hr|); hr < 0 always in the forward direction
       const float th = hv[k] < 0.0f ? kPi + at : kPi - at;
@@ -222,20 +222,26 @@ __device__ __forceinline__ void mixture4(const Plane& P, float zr, float zv, flo
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < N; ++k) {
       S_sp += sp[k];
       raw[4 * k] = al[k]; raw[4 * k + 1] = be[k]; raw[4 * k + 2] = omw[k]; raw[4 * k + 3] = sp[k];
     }
   }
 }
 
+template <bool FWD>
+__device__ __forceinline__ void mixture4(const Plane& P, float zr, float zv, float raw[16], float& S_sp, float& S_th, float& S_f) {
+  mixtureN<4, FWD>(P, zr, zv, raw, S_sp, S_th, S_f);
+}
+
 // Bisection probe of four prepared components at the in-plane point (zr, zv) = (cos t, sin t): stage-wise like mixture4.
 // prm[16] = (alpha', beta', 1 - |w'|^2, weight) x 4; accumulates sum_k weight_k theta_k(z).  Full-circle atan2: during the
 // bisection z sweeps [pi/2, 3pi/2] and h may land anywhere (flow/mobiusflow.py:226-245).
-__device__ __forceinline__ void probe4(float zr, float zv, const float prm[16], float& Fs) {
-  float hr[4], hv[4], ay[4], ax[4], q[4], p[4];
+template <int N>
+__device__ __forceinline__ void probeN(float zr, float zv, const float* prm, float& Fs) {
+  float hr[N], hv[N], ay[N], ax[N], q[N], p[N];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < N; ++k) {
     const float al = prm[4 * k], be = prm[4 * k + 1];
     const float dr = zr - al, dv = zv - be;
     const float f = prm[4 * k + 2] * rcp_approx(fmaf(dv, dv, dr * dr));
@@ -245,10 +251,10 @@ __device__ __forceinline__ void probe4(float zr, float zv, const float prm[16], 
     ax[k] = fabsf(hr[k]);
   }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) q[k] = fminf(ay[k], ax[k]) * rcp_approx(fmaxf(ay[k], ax[k]));
+  for (int k = 0; k < N; ++k) q[k] = fminf(ay[k], ax[k]) * rcp_approx(fmaxf(ay[k], ax[k]));
 #pragma unroll
-  for (int k = 0; k < 4; ++k) p[k] = -0.0024470302741974592f;
-#define RNF_HORNER(cf) _Pragma("unroll") for (int k = 0; k < 4; ++k) p[k] = fmaf(p[k], q[k] * q[k], cf)
+  for (int k = 0; k < N; ++k) p[k] = -0.0024470302741974592f;
+#define RNF_HORNER(cf) _Pragma("unroll") for (int k = 0; k < N; ++k) p[k] = fmaf(p[k], q[k] * q[k], cf)
   RNF_HORNER(0.013750280253589153f);
   RNF_HORNER(-0.03627016767859459f);
   RNF_HORNER(0.06284360587596893f);
@@ -259,7 +265,7 @@ __device__ __forceinline__ void probe4(float zr, float zv, const float prm[16], 
   RNF_HORNER(-0.3333333134651184f);
 #undef RNF_HORNER
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < N; ++k) {
     float at = fmaf(p[k] * (q[k] * q[k]), q[k], q[k]);
     at = ay[k] > ax[k] ? 1.5707963267948966f - at : at;
     at = hr[k] < 0.0f ? kPi - at : at;
@@ -267,5 +273,7 @@ __device__ __forceinline__ void probe4(float zr, float zv, const float prm[16], 
     Fs = fmaf(prm[4 * k + 3], th, Fs);
   }
 }
+
+__device__ __forceinline__ void probe4(float zr, float zv, const float prm[16], float& Fs) { probeN<4>(zr, zv, prm, Fs); }
 
 }  // namespace rnf

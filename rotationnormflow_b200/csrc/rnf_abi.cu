@@ -25,12 +25,13 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 long long* g_trace = nullptr;
 
-bool valid_mode(int m) { return m == RNF_MLP_FP32 || m == RNF_MLP_TC; }
+bool valid_mode(int m) { return m == RNF_MLP_FP32 || m == RNF_MLP_TC || m == RNF_MLP_TC_ROW; }
 
 }  // namespace
 
 namespace rnf {
 cudaError_t launch_flow_tc(const FlowArgs& a, bool inverse, int sm_count, cudaStream_t st);
+cudaError_t launch_flow_row(const FlowArgs& a, bool inverse, int sm_count, cudaStream_t st);
 bool flow_tc_supported(const rnf_flow* f);
 }  // namespace rnf
 
@@ -160,7 +161,8 @@ static int run_rows(rnf_flow* f, bool inverse, const float* R_in, int64_t N, con
   if (mlp_mode != RNF_MLP_FP32) {
     if (!rnf::flow_tc_supported(f)) return fail(RNF_ESTATE, "%s: model was packed without the tensor-core weight image", who);
     a.n_tiles = (N + 127) / 128;
-    e = rnf::launch_flow_tc(a, inverse, f->sm_count, (cudaStream_t)stream);
+    e = mlp_mode == RNF_MLP_TC_ROW ? rnf::launch_flow_row(a, inverse, f->sm_count, (cudaStream_t)stream)
+                                   : rnf::launch_flow_tc(a, inverse, f->sm_count, (cudaStream_t)stream);
   } else {
     a.n_tiles = (N + rnf::kV1Threads - 1) / rnf::kV1Threads;
     e = rnf::launch_flow_v1(a, inverse, f->sm_count, (cudaStream_t)stream);
@@ -228,7 +230,8 @@ int rnf_grid_logprob(rnf_flow* f, const float* grid_dev, int64_t G, int64_t g_in
     if (!rnf::flow_tc_supported(f)) return fail(RNF_ESTATE, "rnf_grid_logprob: model was packed without the tensor-core weight image");
     a.tiles_per_image = (G + 127) / 128;
     a.n_tiles = a.tiles_per_image * B;
-    e = rnf::launch_flow_tc(a, false, f->sm_count, (cudaStream_t)stream);
+    e = mlp_mode == RNF_MLP_TC_ROW ? rnf::launch_flow_row(a, false, f->sm_count, (cudaStream_t)stream)
+                                   : rnf::launch_flow_tc(a, false, f->sm_count, (cudaStream_t)stream);
   } else {
     a.tiles_per_image = (G + rnf::kV1Threads - 1) / rnf::kV1Threads;
     a.n_tiles = a.tiles_per_image * B;

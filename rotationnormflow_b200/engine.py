@@ -27,7 +27,7 @@ TC_AVAILABLE = True    # csrc/flow_tc.cu: tcgen05 conditioner (forward, inverse 
 TC_WEIGHT_SCALE = 1.0    # fp16 hi/lo weight planes are stored unscaled (biases ride along as a K=16 block, see pack_mobius_tc)
 MOB_TC_FLOATS = (3 * (2 * 8192 + 64 * 32) + (2 * 32768 + 256 * 32) + 1024) // 4   # kTcImageBytes / 4 in csrc/tc_common.cuh
 
-_MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC}
+_MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC, "tc_row": _cabi.RNF_MLP_TC_ROW}
 
 
 def default_mlp_mode() -> str:
