@@ -12,6 +12,15 @@
 namespace rnf {
 namespace {
 
+#ifndef RNF_TC_TRACE
+#define RNF_TC_TRACE 0
+#endif
+#if RNF_TC_TRACE
+#define TRACE(i) do { if (tr_on) tr[(i)] = clock64(); } while (0)
+#else
+#define TRACE(i) do { } while (0)
+#endif
+
 constexpr int kThreads = 256;
 constexpr int kRows = 128;                        // rows per tile = TMEM lanes = threads per tile
 
@@ -208,6 +217,12 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
       make_frame_fast(x, y, P);
       const float zr = dot3(x, P.r), zv = dot3(x, P.v);   // in-plane coordinates of the moving column
       const float* cimg = (L.cond_slot >= 0 && cond_img != nullptr) ? cond_img + (int64_t)L.cond_slot * kH : nullptr;
+#if RNF_TC_TRACE
+      const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && elected && step >= 40 && step < 48;
+      long long* tr = a.trace + ((tile * 8 + (step - 40)) * 32);
+#endif
+      TRACE(0);
+      TRACE(1);
       const int abuf = (int)(step & 1);
       const int mob_n1 = mob_cur + 1 >= n_mob ? mob_cur + 1 - n_mob : mob_cur + 1;
       const int mob_n2 = mob_n1 + 1 >= n_mob ? mob_n1 + 1 - n_mob : mob_n1 + 1;
@@ -232,12 +247,14 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
         tmem_st32(tm + 64 + 32 * h, h0);
         store_a32(a_hi, a_lo, rowi, h, h0);          // ReLU happens inside the fp16 split
       }
+      TRACE(2);
       // ---- three hidden layers on the tensor core ----
 #pragma unroll 1
       for (int l = 0; l < 3; ++l) {
         fence_proxy_async();
         tc_fence_before();
         named_bar(bar_tile, 128);
+        TRACE(3 + 4 * l);
         if (issuer_warp) {
           mbar_wait(bars + 8 * (BAR_W_FULL + l), (par_w >> l) & 1u);
           tc_fence_after();
@@ -249,9 +266,11 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
           }
           __syncwarp();
         }
+        TRACE(4 + 4 * l);
         mbar_wait(bar_mma0, par_mma0);
         par_mma0 ^= 1;
         tc_fence_after();
+        TRACE(5 + 4 * l);
         // W_l is dead once BOTH tiles' GEMM l has completed: the second tile to get here refills it for the next layer
         if (elected && (atomicAdd(&s_cnt[l], 1) & 1) && step + 1 < total_steps) load_piece(mob_n1, l, 0);
 #pragma unroll
@@ -266,11 +285,13 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
           }
           store_a32(a_hi, a_lo, rowi, h, acc);
         }
+        TRACE(6 + 4 * l);
       }
       // ---- fc_last: two N = 128 chunks, own barrier each ----
       fence_proxy_async();
       tc_fence_before();
       named_bar(bar_tile, 128);
+      TRACE(15);
       if (issuer_warp) {
         mbar_wait(bars + 8 * (BAR_W_FULL + 3), (par_w >> 3) & 1u);
         tc_fence_after();
@@ -290,9 +311,11 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
       float S_sp = 0.0f, S_th = 0.0f, S_f = 0.0f;
       {
         float bufA[32], bufB[32];
+        TRACE(16);
         mbar_wait(bar_mma0, par_mma0);               // chunk A: columns 0..127
         par_mma0 ^= 1;
         tc_fence_after();
+        TRACE(17);
         tmem_ld32_async(tm, bufA);
         tmem_ld_wait32(bufA);
 #pragma unroll 1
@@ -315,6 +338,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
           if (j < 3) tmem_ld_wait32(bufA);
         }
       }
+      TRACE(18);
+      TRACE(19);
       // W4 is dead once both chunks of BOTH tiles have completed; the aux buffer once both tiles are past their first layer
       if (elected) {
         if ((atomicAdd(&s_cnt[3], 1) & 1) && step + 1 < total_steps) load_piece(mob_n1, 3, 0);
@@ -374,6 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
       normalize3_fast(nz);
       set_col(R, p0, nx);
       set_col(R, p2, nz);
+      TRACE(20);
       tc_fence_before();                             // my TMEM reads of this layer are ordered before the next layer's barrier
       ++step;
       mob_cur = mob_n1;

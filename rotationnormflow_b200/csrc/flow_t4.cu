@@ -1,0 +1,460 @@
+// flow_t4.cu -- forward / grid flow kernel with FOUR 128-rotation tiles in flight per SM (tcgen05 + TMEM), sm_100a.
+//
+// flow_tc.cu / flow_row.cu keep two tiles per SM: their activations go to the tensor core through 32 KB of shared memory per
+// tile and fc_last needs 256 TMEM columns per tile.  ncu on those kernels: issue slots 58-65 % active, tensor pipe 29 %, the
+// rest is exposed latency of the dependent GEMM round trips (15 % of the samples sit in the mbarrier wait) -- two tiles are not
+// enough independent work.  This kernel makes a tile small enough for four:
+//   * the A operand (ReLU'd activations, fp16 hi / lo planes) lives in TENSOR MEMORY: tcgen05.mma in its TS form reads row r
+//     from lane r, K elements (2c, 2c+1) packed in column c.  A thread writes its own row with tcgen05.st -- no shared-memory
+//     staging, no swizzle arithmetic, no proxy fence per GEMM.  64 columns per tile.
+//   * fc_last is issued as four N = 64 chunks (16 mixture components each) into ONE 64-column accumulator that is drained into
+//     registers before the next chunk is issued.  64 columns per tile; 4 x (64 + 64) = the 512 columns of an SM.
+//   * fc_first (K = 3, flow/condition.py:25) and the residual  relu_last(x0 + x3)  (flow/condition.py:29) run on the tensor
+//     core as well: every GEMM starts with one K = 16 MMA of a per-rotation block  Y = (1, 1, y_hi, y_lo, y_hi, 1, 1, 0, 0, 0)
+//     against a per-layer block (b_hi, b_lo, W0_hi, W0_hi, W0_lo, b0_hi, b0_lo, ...) (engine._bias_block), which yields the
+//     bias, W0.y (error-compensated) and, in the last hidden layer, x0 again -- no stash of x0, no FMA loop on the CUDA cores.
+//     The per-image term  c = W_f.feature  (hoisted, rnf_flow_condition) enters through one more K = 16 MMA against a per-tile
+//     block (c_hi, c_lo) in grid mode (a tile never straddles images); in row mode it is added in the epilogue.
+// One thread owns one rotation (512 threads = 4 tiles x 128 rows): nothing is computed twice, nothing is exchanged.
+// The bisection of Flow.inverse needs its 256 prepared parameters resident per row and stays in flow_row.cu.
+#include "tc_common.cuh"
+
+namespace rnf {
+namespace {
+
+#ifndef RNF_TC_TRACE
+#define RNF_TC_TRACE 0
+#endif
+#if RNF_TC_TRACE
+#define TRACE(i) do { if (tr_on) tr[(i)] = clock64(); } while (0)
+#else
+#define TRACE(i) do { } while (0)
+#endif
+
+constexpr int kTiles = 4;
+constexpr int kThreads = kTiles * 128;
+constexpr int kRows = 128;
+
+// shared memory (bytes from a 1024-aligned base)
+constexpr int kOffW = 0;                                  // W1 | W2 | W3 pieces
+constexpr int kOffLastW = kHidW;                          // W4 piece
+constexpr int kOffAux = kOffLastW + kLastW;               // aux piece, double buffered on the layer parity
+constexpr int kOffY = kOffAux + 2 * kAuxStride;           // [tile] Y block [128 x 16] fp16, no swizzle (4 KB)
+constexpr int kOffC = kOffY + kTiles * 4096;              // [tile] per-image block [64 x 16] fp16, no swizzle (2 KB)
+constexpr int kOffRed = kOffC + kTiles * 2048;            // [tile] reduction scratch
+constexpr int kOffBar = kOffRed + kTiles * 128;
+constexpr int kOffMisc = kOffBar + 8 * 16;
+constexpr int kSmemBytes = kOffMisc + 32 + 64 * 8;
+constexpr int kSmemAlloc = kSmemBytes + 1024;
+static_assert(kOffLastW % 1024 == 0 && kW1Bytes % 1024 == 0, "UMMA SW128 tiles need 1024 B alignment");
+static_assert(kOffY % 16 == 0 && kOffC % 16 == 0 && kOffAux % 16 == 0, "no-swizzle blocks need 16 B alignment");
+
+enum { BAR_W_FULL = 0 /* W1,W2,W3,W4 */, BAR_AUX_FULL = 4 /* [2] */, BAR_MMA = 6 /* [tile] */, BAR_COUNT = 10 };
+
+// TMEM columns of a tile
+constexpr uint32_t kColAhi = 0, kColAlo = 32, kColD = 64, kColsPerTile = 128;
+
+// D (+)= A[tmem] . B[smem desc]^T : TS form of tcgen05.mma (A: lane = row, 16-bit K elements packed two per column)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo32, uint32_t desc_hi32, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 db, {%2, %3};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo32), "r"(desc_hi32), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 3-product split GEMM on top of an initialised accumulator: D += Alo.Whi + Ahi.Wlo + Ahi.Whi   (K = 64 in four K = 16 steps;
+// a step is 8 TMEM columns on the A side, 32 B = +2 descriptor units on the B side)
+__device__ __forceinline__ void issue_split_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t idesc) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_f16_ts(d, a_lo + 8 * k, b_hi + 2 * k, kDescHi, idesc, 1);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_f16_ts(d, a_hi + 8 * k, b_lo + 2 * k, kDescHi, idesc, 1);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) umma_f16_ts(d, a_hi + 8 * k, b_hi + 2 * k, kDescHi, idesc, 1);
+}
+
+__device__ __forceinline__ uint32_t pack_h2(__half lo, __half hi) {
+  const __half2 h = __halves2half2(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// Epilogue of one GEMM for 32 of my row's 64 hidden units: accumulator -> (+ c) -> ReLU -> fp16 hi / lo -> A operand in TMEM
+__device__ __forceinline__ void epilogue32(uint32_t tm, int h, const float* cadd) {
+  float acc[32];
+  tmem_ld32(tm + kColD + 32 * h, acc);
+  if (cadd != nullptr) {
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+      const float4 c = __ldg(reinterpret_cast<const float4*>(cadd + 32 * h) + j4);
+      acc[4 * j4] += c.x; acc[4 * j4 + 1] += c.y; acc[4 * j4 + 2] += c.z; acc[4 * j4 + 3] += c.w;
+    }
+  }
+  float hi[16], lo[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    uint32_t uh, ul;
+    relu_split2(acc[2 * e], acc[2 * e + 1], uh, ul);       // K element 2e in the low half, 2e + 1 in the high half
+    hi[e] = __uint_as_float(uh);
+    lo[e] = __uint_as_float(ul);
+  }
+  tmem_st16(tm + kColAhi + 16 * h, hi);
+  tmem_st16(tm + kColAlo + 16 * h, lo);
+}
+
+template <bool GRID>
+__global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int tile = warp >> 2;                        // 0..3
+  const int rowi = (warp & 3) * 32 + lane;           // row inside the tile = TMEM lane
+  const bool elected = rowi == 0;                    // counts the tile's consumption of weight pieces, refills them
+  const bool issuer_warp = (warp & 3) == 0;          // warp-uniform: issues this tile's MMAs
+  const uint32_t bars = smem_u32(smem + kOffBar);
+
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kOffMisc);
+  int* s_cnt = reinterpret_cast<int*>(smem + kOffMisc + 4);                // tiles done with: [0..2] W1..W3, [3] W4, [4 + buf] aux
+  long long* s_moff = reinterpret_cast<long long*>(smem + kOffMisc + 32);
+
+  int n_mob = 0;
+  for (int i = 0; i < a.n_layers; ++i)
+    if (a.layers[i].kind == RNF_LAYER_MOBIUS) {
+      if (tid == 0) s_moff[n_mob] = a.layers[i].w_off_tc;
+      ++n_mob;
+    }
+  if (tid == 0) {
+    for (int i = 0; i < BAR_COUNT; ++i) mbar_init(bars + 8 * i, 1);
+    for (int i = 0; i < 6; ++i) s_cnt[i] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // Y and per-image blocks start out as zeros (the unused K slots stay zero for the whole kernel)
+  for (int i = tid; i < (kTiles * (4096 + 2048)) / 16; i += kThreads) reinterpret_cast<uint4*>(smem + kOffY)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tm_tile = tmem_base + (uint32_t)tile * kColsPerTile;                   // lane 0 of the tile (MMA addresses)
+  const uint32_t tm = tm_tile + ((uint32_t)((warp & 3) * 32) << 16);                    // my warp's lane quarter
+
+  const int64_t n_groups = (a.n_tiles + kTiles - 1) / kTiles;
+  const int64_t my_items = blockIdx.x < n_groups ? (n_groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const int64_t total_steps = my_items * n_mob;
+  const uint8_t* wbytes = reinterpret_cast<const uint8_t*>(a.weights);
+  auto load_piece = [&](int mob_idx, int piece, int abuf) {   // piece 0..2 = W1..W3, 3 = W4, 4 = aux (into buffer abuf)
+    const uint8_t* src = wbytes + s_moff[mob_idx] * 4;
+    uint32_t dst, bytes, bar;
+    if (piece < 3) { src += piece * kW1Bytes; dst = kOffW + piece * kW1Bytes; bytes = kW1Bytes; bar = BAR_W_FULL + piece; }
+    else if (piece == 3) { src += kHidW; dst = kOffLastW; bytes = kLastW; bar = BAR_W_FULL + 3; }
+    else { src += kHidW + kLastW; dst = kOffAux + abuf * kAuxStride; bytes = kAuxBytes; bar = BAR_AUX_FULL + abuf; }
+    mbar_expect_tx(bars + 8 * bar, bytes);
+    bulk_g2s(smem_u32(smem + dst), src, bytes, bars + 8 * bar);
+  };
+  if (tid == 0 && total_steps > 0) {
+    for (int piece = 0; piece < 4; ++piece) load_piece(0, piece, 0);
+    load_piece(0, 4, 0);
+    if (total_steps > 1) load_piece(n_mob > 1 ? 1 : 0, 4, 1);
+  }
+
+  uint8_t* y_blk = smem + kOffY + tile * 4096;
+  uint8_t* c_blk = smem + kOffC + tile * 2048;
+  const uint32_t y_d = umma_desc_lo_ns(smem_u32(y_blk)), c_d = umma_desc_lo_ns(smem_u32(c_blk));
+  const uint32_t w_hid_d = umma_desc_lo(smem_u32(smem + kOffW)), w_last_d = umma_desc_lo(smem_u32(smem + kOffLastW));
+  const uint32_t bias_hid_d = umma_desc_lo_ns(smem_u32(smem + kOffW + 16384)), bias_last_d = umma_desc_lo_ns(smem_u32(smem + kOffLastW + 65536));
+  const uint32_t aux_blk_d = umma_desc_lo_ns(smem_u32(smem + kOffAux + kAuxFirst));
+  const int bar_tile = 1 + tile;                     // named barrier of the tile's 128 threads
+  const uint32_t bar_mma = bars + 8 * (BAR_MMA + tile);
+  uint32_t par_mma = 0, par_w = 0;
+  int64_t step = 0;
+  int mob_cur = 0;
+  constexpr uint32_t kIdesc = umma_idesc(128, 64);
+
+  // Hand-over of the tile's accumulator / A operand to the tensor core: every thread orders its TMEM accesses before the
+  // barrier; only the issuing warp waits there (the others go straight to the mbarrier of the GEMM being issued).
+  auto hand_over = [&]() {
+    tc_fence_before();
+    if (issuer_warp) named_bar(bar_tile, 128); else named_arrive(bar_tile, 128);
+  };
+  auto wait_mma = [&]() {
+    mbar_wait(bar_mma, par_mma);
+    par_mma ^= 1;
+    tc_fence_after();
+  };
+
+  for (int64_t item = 0; item < my_items; ++item) {
+    const int64_t tile_idx = kTiles * (blockIdx.x + item * (int64_t)gridDim.x) + tile;
+    int64_t row = 0, img = 0, g = 0;
+    bool valid = false;
+    float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+    if (tile_idx < a.n_tiles) {
+      if (GRID) {
+        img = tile_idx / a.tiles_per_image;
+        g = (tile_idx % a.tiles_per_image) * kRows + rowi;
+        valid = g < a.G;
+        row = img * a.G + g;
+        if (valid) {
+          float Gm[9];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) Gm[i] = __ldg(a.R_in + g * 9 + i);
+          if (a.offset != nullptr) {                 // samples = grid @ random_rot (eval.py:439-440)
+            float O[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) O[i] = __ldg(a.offset + i);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+                R[3 * i + j] = fmaf(Gm[3 * i + 2], O[6 + j], fmaf(Gm[3 * i + 1], O[3 + j], Gm[3 * i] * O[j]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) R[i] = Gm[i];
+          }
+        }
+      } else {
+        row = tile_idx * kRows + rowi;
+        valid = row < a.N;
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) R[i] = __ldg(a.R_in + row * 9 + i);
+          if (a.cond != nullptr) img = a.feat_index != nullptr ? (int64_t)__ldg(a.feat_index + row) : row / a.rows_per_image;
+        }
+      }
+    }
+    const float* cond_img = a.cond != nullptr ? a.cond + img * a.cond_stride : nullptr;
+    float ldj = 0.0f;
+
+#pragma unroll 1
+    for (int li = 0; li < a.n_layers; ++li) {
+      const LayerDev L = a.layers[li];
+      if (L.kind != RNF_LAYER_MOBIUS) {
+        const float* W = L.cond_slot >= 0 ? cond_img + (int64_t)a.n_mobius_slots * kH + (int64_t)L.cond_slot * kAffFloats
+                                          : a.weights + L.w_off;
+        float Wr[17];
+#pragma unroll
+        for (int i = 0; i < 17; ++i) Wr[i] = __ldg(W + i);
+        const float loglen = quat_affine_fast(Wr, R);
+        if (L.has_ldj) ldj += Wr[16] - 4.0f * loglen;
+        continue;
+      }
+      // ================================ Mobius layer ================================
+      const int p0 = L.perm, p1 = (L.perm + 1) % 3, p2 = (L.perm + 2) % 3;
+      float x[3], y[3];
+      Plane P;
+      get_col(R, p0, x);
+      get_col(R, p1, y);
+      make_frame_fast(x, y, P);
+      const float zr = dot3(x, P.r), zv = dot3(x, P.v);   // in-plane coordinates of the moving column
+      const float* cimg = (L.cond_slot >= 0 && cond_img != nullptr) ? cond_img + (int64_t)L.cond_slot * kH : nullptr;
+      const bool c_by_mma = GRID && cimg != nullptr;      // warp- and tile-uniform
+      const float* cadd = GRID ? nullptr : cimg;
+#if RNF_TC_TRACE
+      const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && elected && step >= 40 && step < 48;
+      long long* tr = a.trace + ((tile * 8 + (step - 40)) * 32);
+#endif
+      TRACE(0);
+      const int abuf = (int)(step & 1);
+      const int mob_n1 = mob_cur + 1 >= n_mob ? mob_cur + 1 - n_mob : mob_cur + 1;
+      const int mob_n2 = mob_n1 + 1 >= n_mob ? mob_n1 + 1 - n_mob : mob_n1 + 1;
+
+      // ---- my row of the Y block: (1, 1, y_hi, y_lo | y_hi, 1, 1, 0, 0, 0); per-image block in grid mode ----
+      {
+        __half yh[3], yl[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          yh[i] = __float2half_rn(y[i]);
+          yl[i] = __float2half_rn(y[i] - __half2float(yh[i]));
+        }
+        const __half one = __float2half_rn(1.0f), zero = __float2half_rn(0.0f);
+        uint8_t* yrow = y_blk + (rowi >> 3) * 256 + (rowi & 7) * 16;
+        *reinterpret_cast<uint4*>(yrow) = make_uint4(pack_h2(one, one), pack_h2(yh[0], yh[1]), pack_h2(yh[2], yl[0]), pack_h2(yl[1], yl[2]));
+        *reinterpret_cast<uint4*>(yrow + 128) = make_uint4(pack_h2(yh[0], yh[1]), pack_h2(yh[2], one), pack_h2(one, zero), 0u);
+        if (c_by_mma && rowi < 64) {
+          const float cv = __ldg(cimg + rowi);
+          const __half ch = __float2half_rn(cv);
+          const __half cl = __float2half_rn(cv - __half2float(ch));
+          *reinterpret_cast<uint32_t*>(c_blk + (rowi >> 3) * 256 + (rowi & 7) * 16) = pack_h2(ch, cl);
+        }
+      }
+      fence_proxy_async();
+      hand_over();
+      TRACE(1);
+      // ---- fc_first and three hidden layers: four dependent GEMM round trips ----
+#pragma unroll 1
+      for (int l = 0; l < 4; ++l) {
+        if (issuer_warp) {
+          if (l == 0) mbar_wait(bars + 8 * (BAR_AUX_FULL + abuf), (uint32_t)((step >> 1) & 1));
+          else mbar_wait(bars + 8 * (BAR_W_FULL + l - 1), (par_w >> (l - 1)) & 1u);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t d = tm_tile + kColD;
+            if (l == 0) {
+              umma_f16(d, y_d, aux_blk_d + abuf * (kAuxStride >> 4), kDescHiNS, kIdesc, 0);
+            } else {
+              const uint32_t wb = w_hid_d + (l - 1) * (kW1Bytes >> 4);
+              umma_f16(d, y_d, bias_hid_d + (l - 1) * (kW1Bytes >> 4), kDescHiNS, kIdesc, 0);
+              issue_split_ts(d, tm_tile + kColAhi, tm_tile + kColAlo, wb, wb + (8192 >> 4), kIdesc);
+            }
+            if (c_by_mma && (l == 0 || l == 3)) umma_f16(d, y_d, c_d, kDescHiNS, kIdesc, 1);
+            umma_commit(bar_mma);
+          }
+          __syncwarp();
+        }
+        TRACE(2 + 3 * l);
+        wait_mma();
+        TRACE(3 + 3 * l);
+        // a piece is dead once ALL tiles' GEMM that reads it has completed: the last tile to get here refills it
+        if (elected) {
+          if (l == 0) { if ((atomicAdd(&s_cnt[4 + abuf], 1) & 3) == 3 && step + 2 < total_steps) load_piece(mob_n2, 4, abuf); }
+          else if ((atomicAdd(&s_cnt[l - 1], 1) & 3) == 3 && step + 1 < total_steps) load_piece(mob_n1, l - 1, 0);
+        }
+        const float* ca = (l == 0 || l == 3) ? cadd : nullptr;
+        epilogue32(tm, 0, ca);
+        epilogue32(tm, 1, ca);
+        hand_over();
+        TRACE(4 + 3 * l);
+      }
+      // ---- fc_last in four N = 64 chunks through the single accumulator; 16 mixture components per chunk ----
+      auto issue_chunk = [&](int c) {               // issuing warp only, right after the hand-over barrier
+        if (c == 0) mbar_wait(bars + 8 * (BAR_W_FULL + 3), (par_w >> 3) & 1u);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t d = tm_tile + kColD;
+          const uint32_t wb = w_last_d + c * (8192 >> 4);                  // rows 64c .. 64c+63 of the hi plane
+          umma_f16(d, y_d, bias_last_d + c * (2048 >> 4), kDescHiNS, kIdesc, 0);
+          issue_split_ts(d, tm_tile + kColAhi, tm_tile + kColAlo, wb, wb + (32768 >> 4), kIdesc);
+          umma_commit(bar_mma);
+        }
+        __syncwarp();
+      };
+      if (issuer_warp) issue_chunk(0);
+      float S_sp = 0.0f, S_th = 0.0f, S_f = 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float buf0[16], buf1[16];
+        wait_mma();
+        TRACE(14 + c);
+        tmem_ld16_async(tm + kColD, buf0);
+        tmem_ld16_async(tm + kColD + 16, buf1);
+        tmem_ld_wait16(buf0);
+        mixture4<true>(P, zr, zv, buf0, S_sp, S_th, S_f);
+        tmem_ld16_async(tm + kColD + 32, buf0);
+        tmem_ld_wait16(buf1);
+        mixture4<true>(P, zr, zv, buf1, S_sp, S_th, S_f);
+        tmem_ld16_async(tm + kColD + 48, buf1);
+        tmem_ld_wait16(buf0);
+        tmem_ld_wait16(buf1);
+        if (c < 3) {                                  // accumulator drained: the next chunk runs under the math below
+          hand_over();
+          if (issuer_warp) issue_chunk(c + 1);
+        }
+        mixture4<true>(P, zr, zv, buf0, S_sp, S_th, S_f);
+        mixture4<true>(P, zr, zv, buf1, S_sp, S_th, S_f);
+      }
+      if (issuer_warp) par_w ^= 0xFu;
+      if (elected && (atomicAdd(&s_cnt[3], 1) & 3) == 3 && step + 1 < total_steps) load_piece(mob_n1, 3, 0);
+      TRACE(18);
+      float nx[3], nz[3];
+      const float inv_sp = rcp_nr(S_sp);
+      circle_point(P.r, P.v, S_th * inv_sp, nx);
+      ldj += logf(S_f * inv_sp);
+      cross3(nx, y, nz);
+      normalize3_fast(nz);
+      set_col(R, p0, nx);
+      set_col(R, p2, nz);
+      TRACE(19);
+      ++step;
+      mob_cur = mob_n1;
+    }
+
+    // ================================ outputs ================================
+    if (!GRID) {
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) a.R_out[row * 9 + i] = R[i];
+        a.ldj_out[row] = ldj;
+      }
+    } else if (tile_idx < a.n_tiles) {
+      float lp = ldj;
+      if (a.fisher_A != nullptr) {
+        float tr = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) tr = fmaf(__ldg(a.fisher_A + img * 9 + i), R[i], tr);
+        lp += tr - __ldg(a.fisher_c + img);
+      }
+      if (!valid) lp = -INFINITY;
+      if (a.logp_out != nullptr && valid) a.logp_out[row] = lp;
+      float* s_v = reinterpret_cast<float*>(smem + kOffRed + tile * 128);
+      long long* s_i = reinterpret_cast<long long*>(smem + kOffRed + tile * 128 + 32);
+      const int w4 = warp & 3;
+      const int bar_red = 5 + tile;
+      float bv = lp;
+      long long bi = valid ? (long long)g : 0x7fffffffffffffffLL;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { s_v[w4] = bv; s_i[w4] = bi; }
+      named_bar(bar_red, 128);
+      bv = s_v[0]; bi = s_i[0];
+#pragma unroll
+      for (int w = 1; w < 4; ++w) {
+        const float ov = s_v[w];
+        const long long oi = s_i[w];
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      const float m = bv;
+      float e = (valid && m > -INFINITY) ? expf(lp - m) : 0.0f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+      named_bar(bar_red, 128);
+      if (lane == 0) s_v[w4] = e;
+      named_bar(bar_red, 128);
+      if (rowi == 0) {
+        const float s = (s_v[0] + s_v[1]) + (s_v[2] + s_v[3]);
+        float* p = a.part + tile_idx * 4;
+        p[0] = m;
+        p[1] = s;
+        p[2] = __int_as_float((int)(bi & 0xffffffffLL));
+        p[3] = __int_as_float((int)(bi >> 32));
+      }
+      named_bar(bar_red, 128);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_flow_t4(const FlowArgs& a, int sm_count, cudaStream_t st) {
+  const bool grid_mode = a.G > 0;
+  void (*kern)(const FlowArgs) = grid_mode ? flow_t4_kernel<true> : flow_t4_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc);
+  if (e != cudaSuccess) return e;
+  if (a.n_tiles <= 0) return cudaSuccess;
+  const int64_t groups = (a.n_tiles + kTiles - 1) / kTiles;
+  const int64_t grid = groups < sm_count ? groups : sm_count;
+  kern<<<(unsigned)grid, kThreads, kSmemAlloc, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace rnf

@@ -15,7 +15,7 @@ namespace rnf {
 // Packed global image of one Mobius conditioner (== the shared-memory pieces, one bulk copy each):
 //   W1 | W2 | W3 : each [hi 64x64 | lo 64x64] fp16 K-major SWIZZLE_128B, then the bias block [64 x 16] fp16 (no swizzle)
 //   W4           : [hi 256x64 | lo 256x64] fp16 SW128 (outputs permuted: component c owns columns 4c..4c+3), bias block [256 x 16]
-//   aux          : first[64][4] fp32  (W0[:, :3] and b0 of fc_first)
+//   aux          : first[64][4] fp32  (W0[:, :3] and b0 of fc_first), then the fc_first block [64 x 16] fp16 (no swizzle)
 // A bias block holds (b_hi, b_lo) in its K columns 0 and 1; multiplied by a constant [128 x 16] tile with ones in those two
 // columns it initialises the accumulator with the bias, so the CUDA cores never touch a bias or a scale factor.
 constexpr int kBiasBlkHid = 64 * 32;
@@ -23,9 +23,10 @@ constexpr int kBiasBlkLast = 256 * 32;
 constexpr int kW1Bytes = 2 * 8192 + kBiasBlkHid;  // 18432
 constexpr int kHidW = 3 * kW1Bytes;               // 55296
 constexpr int kLastW = 2 * 32768 + kBiasBlkLast;  // 73728
-constexpr int kAuxBytes = 1024;
-constexpr int kAuxStride = 1024;
-constexpr int kTcImageBytes = kHidW + kLastW + kAuxBytes;   // 130048
+constexpr int kAuxFirst = 1024;                   // first[64][4] fp32
+constexpr int kAuxBytes = kAuxFirst + kBiasBlkHid; // + fc_first block [64 x 16] fp16 (flow_t4.cu)
+constexpr int kAuxStride = kAuxBytes;             // 3072
+constexpr int kTcImageBytes = kHidW + kLastW + kAuxBytes;   // 132096
 
 // ------------------------------------------------ PTX wrappers ---------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

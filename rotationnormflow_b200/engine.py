@@ -25,9 +25,9 @@ CAFF_FLOATS = 64 + 3 * (64 * 64 + 64) + 16 * 64 + 16
 
 TC_AVAILABLE = True    # csrc/flow_tc.cu: tcgen05 conditioner (forward, inverse and grid mode)
 TC_WEIGHT_SCALE = 1.0    # fp16 hi/lo weight planes are stored unscaled (biases ride along as a K=16 block, see pack_mobius_tc)
-MOB_TC_FLOATS = (3 * (2 * 8192 + 64 * 32) + (2 * 32768 + 256 * 32) + 1024) // 4   # kTcImageBytes / 4 in csrc/tc_common.cuh
+MOB_TC_FLOATS = (3 * (2 * 8192 + 64 * 32) + (2 * 32768 + 256 * 32) + 1024 + 64 * 32) // 4   # kTcImageBytes / 4 in csrc/tc_common.cuh
 
-_MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC, "tc_row": _cabi.RNF_MLP_TC_ROW}
+_MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC, "tc_row": _cabi.RNF_MLP_TC_ROW, "tc4": _cabi.RNF_MLP_TC4}
 
 
 def default_mlp_mode() -> str:
@@ -93,35 +93,55 @@ def _split_fp16(W: np.ndarray):
     return hi, lo
 
 
-def _bias_block(b: np.ndarray) -> np.ndarray:
-    """[N] fp32 bias -> [N x 16] fp16 block in the no-swizzle K-major UMMA layout, (b_hi, b_lo) in K columns 0 and 1:
-    element (n, k) at (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2 bytes.  Against the kernel's constant ones tile it yields b."""
+def _hi_lo(x: np.ndarray):
+    hi = x.astype(np.float16)
+    return hi, (x - hi.astype(np.float32)).astype(np.float16)
+
+
+def _bias_block(b: np.ndarray, W0: np.ndarray | None = None, b0: np.ndarray | None = None, b0_slot: int = 11) -> np.ndarray:
+    """[N x 16] fp16 B-operand block in the no-swizzle K-major UMMA layout: element (n, k) at
+    (n/8)*256 + (k/8)*128 + (n%8)*16 + (k%8)*2 bytes.  K slots per output unit n:
+        0, 1   : (b_hi, b_lo)                                  -- bias of the layer
+        2 .. 10: (W0hi[n,:3], W0hi[n,:3], W0lo[n,:3])           -- fc_first columns acting on the conditioning column y
+        b0_slot, b0_slot + 1 : (b0_hi, b0_lo)                   -- fc_first bias (for the residual x0 + x3)
+    The kernels multiply it by a per-rotation [128 x 16] A block.  csrc/flow_tc.cu / flow_row.cu use a constant block with
+    ones in slots 0, 1 (bias only); csrc/flow_t4.cu uses (1, 1, y_hi, y_lo, y_hi, 1, 1, 0, 0, 0), which makes the tensor core
+    evaluate fc_first (flow/condition.py:25) and re-create x0 inside the last hidden GEMM (flow/condition.py:29)."""
     N = b.shape[0]
-    hi = b.astype(np.float16)
-    lo = (b - hi.astype(np.float32)).astype(np.float16)
+    slots = np.zeros((N, 16), dtype=np.float16)
+    slots[:, 0], slots[:, 1] = _hi_lo(b.astype(np.float32))
+    if W0 is not None:
+        whi, wlo = _hi_lo(W0.astype(np.float32))
+        slots[:, 2:5], slots[:, 5:8], slots[:, 8:11] = whi, whi, wlo
+    if b0 is not None:
+        slots[:, b0_slot], slots[:, b0_slot + 1] = _hi_lo(b0.astype(np.float32))
+    n = np.arange(N)[:, None]
+    k = np.arange(16)[None, :]
+    off = ((n // 8) * 256 + (k // 8) * 128 + (n % 8) * 16 + (k % 8) * 2) // 2
     out = np.zeros(N * 16, dtype=np.float16)
-    n = np.arange(N)
-    base = ((n // 8) * 256 + (n % 8) * 16) // 2
-    out[base] = hi
-    out[base + 1] = lo
+    out[off.reshape(-1)] = slots.reshape(-1)
     return out
 
 
 def pack_mobius_tc(cond_sd: dict) -> np.ndarray:
-    """Tensor-core image of one Mobius conditioner = the exact shared-memory pieces of csrc/flow_tc.cu:
-    3 x [hi 64x64 | lo 64x64 fp16 SW128 | bias block 64x16] | [hi 256x64 | lo 256x64 SW128 | bias block 256x16] | first[64][4] fp32
-    returned as float32 words (MOB_TC_FLOATS of them)."""
+    """Tensor-core image of one Mobius conditioner = the exact shared-memory pieces of the tcgen05 kernels:
+    3 x [hi 64x64 | lo 64x64 fp16 SW128 | bias block 64x16] | [hi 256x64 | lo 256x64 SW128 | bias block 256x16]
+    | aux: first[64][4] fp32 (flow_tc / flow_row: fc_first on the CUDA cores), fc_first block 64x16 (flow_t4: on the tensor core)
+    returned as float32 words (MOB_TC_FLOATS of them).  The block of the last hidden layer also carries fc_first (residual)."""
     W0, b0 = _np(cond_sd["fc_first.weight"]), _np(cond_sd["fc_first.bias"])
+    W0y = np.ascontiguousarray(W0[:, :3])
     parts = []
     for j in (1, 3, 5):
         hi, lo = _split_fp16(_np(cond_sd[f"layers.{j}.weight"]))          # nn.Linear weight is [out=N, in=K]: K-major
-        parts += [_umma_k_major_sw128(hi).view(np.float32), _umma_k_major_sw128(lo).view(np.float32),
-                  _bias_block(_np(cond_sd[f"layers.{j}.bias"])).view(np.float32)]
+        b = _np(cond_sd[f"layers.{j}.bias"])
+        blk = _bias_block(b, W0y, b0) if j == 5 else _bias_block(b)
+        parts += [_umma_k_major_sw128(hi).view(np.float32), _umma_k_major_sw128(lo).view(np.float32), blk.view(np.float32)]
     perm = _last_layer_perm(K_SEGMENTS)
     hi, lo = _split_fp16(_np(cond_sd["fc_last.weight"])[perm])
     parts += [_umma_k_major_sw128(hi).view(np.float32), _umma_k_major_sw128(lo).view(np.float32),
               _bias_block(_np(cond_sd["fc_last.bias"])[perm]).view(np.float32)]
-    parts.append(np.concatenate([W0[:, :3], b0[:, None]], axis=1).astype(np.float32).reshape(-1))
+    parts.append(np.concatenate([W0y, b0[:, None]], axis=1).astype(np.float32).reshape(-1))
+    parts.append(_bias_block(b0, W0y).view(np.float32))
     blk = np.concatenate(parts).astype(np.float32, copy=False)
     assert blk.size == MOB_TC_FLOATS
     return blk

@@ -17,7 +17,7 @@ raw.rnf_debug_set_trace.argtypes = [C.c_void_p]
 raw.rnf_debug_set_trace(C.c_void_p(trace.data_ptr()))
 G = rgrid.healpix_grid(5)
 feat = torch.relu(torch.randn(1, 2048)).cuda()
-out = flow.grid_log_prob(G, feat, mlp_mode="tc")
+out = flow.grid_log_prob(G, feat, mlp_mode=os.environ.get("RNF_TRACE_MODE", "tc"))
 torch.cuda.synchronize()
 t = trace.cpu().reshape(2, 8, 32)
 names = {0: "start", 1: "turn", 2: "prologue", 3: "bar1", 4: "iss1", 5: "mma1", 6: "epi1", 7: "bar2", 8: "iss2", 9: "mma2", 10: "epi2",
