@@ -41,9 +41,9 @@ extern "C" {
 
 /* kernel selection for the conditioner MLP (flow/condition.py:24-30) */
 #define RNF_MLP_FP32 0    /* FP32 CUDA-core FMA: the exact-precision path                             */
-#define RNF_MLP_TC 1      /* tcgen05 tensor cores, error-compensated split operands, FP32 accumulate  */
-#define RNF_MLP_TC_ROW 2  /* same arithmetic, one thread per rotation (csrc/flow_row.cu)                */
-#define RNF_MLP_TC4 3     /* forward / grid: four tiles per SM, activations in tensor memory (csrc/flow_t4.cu); inverse: as TC_ROW */
+#define RNF_MLP_TC 1      /* tcgen05 tensor cores, error-compensated split operands, FP32 accumulate: forward / grid with four
+                             tiles per SM and the activations in tensor memory (csrc/flow_t4.cu), inverse as RNF_MLP_TC_ROW */
+#define RNF_MLP_TC_ROW 2  /* same arithmetic, two tiles per SM, activations through shared memory (csrc/flow_row.cu)   */
 
 /*
  * One entry per layer, in module order (index i == `layers.{i}` of the reference state dict).

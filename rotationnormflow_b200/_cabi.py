@@ -18,7 +18,6 @@ RNF_LAYER_AFFINE = 1
 RNF_MLP_FP32 = 0
 RNF_MLP_TC = 1
 RNF_MLP_TC_ROW = 2
-RNF_MLP_TC4 = 3
 
 
 class LayerDesc(C.Structure):

@@ -7,6 +7,7 @@
 // 256 threads per CTA (two 128-rotation tiles, four warps each), up to 255 registers per thread, so the mixture runs eight
 // components at a time stage by stage (eight independent ~200-cycle chains per warp), nothing is computed twice and nothing
 // is exchanged.  Latency hiding comes from instruction-level parallelism instead of extra warps.
+#include "mobius_pair.cuh"
 #include "tc_common.cuh"
 
 namespace rnf {
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
       }
 
       // ---- mixture of all 64 components, 8 at a time straight from TMEM; next 32 columns in flight ----
-      float S_sp = 0.0f, S_th = 0.0f, S_f = 0.0f;
+      f32x2 S_sp2 = 0ull, S_th2 = 0ull, S_f2 = 0ull;   // packed partial sums (even | odd components)
       {
         float bufA[32], bufB[32];
         TRACE(16);
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
         for (int j = 0; j < 4; ++j) {
           tmem_ld32_async(tm + 64 * j + 32, bufB);
           __nanosleep(0);                            // scheduler yield (see flow_tc.cu)
-          mixtureN<8, !INV>(P, zr, zv, bufA, S_sp, S_th, S_f);
+          mixture_pairs<4, !INV>(P, zr, zv, bufA, S_sp2, S_th2, S_f2);
           if (INV) tmem_st32(tm + 64 * j, bufA);
           tmem_ld_wait32(bufB);
           if (j < 3) {
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
             }
             tmem_ld32_async(tm + 64 * j + 64, bufA);
           }
-          mixtureN<8, !INV>(P, zr, zv, bufB, S_sp, S_th, S_f);
+          mixture_pairs<4, !INV>(P, zr, zv, bufB, S_sp2, S_th2, S_f2);
           if (INV) tmem_st32(tm + 64 * j + 32, bufB);
           if (j < 3) tmem_ld_wait32(bufA);
         }
@@ -346,7 +347,9 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
         if ((atomicAdd(&s_cnt[4], 1) & 1) && step + 2 < total_steps) load_piece(mob_n2, 4, abuf);
       }
       float nx[3], nz[3];
+      const float S_sp = hsum(S_sp2);
       if (!INV) {
+        const float S_th = hsum(S_th2), S_f = hsum(S_f2);
         const float inv_sp = rcp_nr(S_sp);
         circle_point(P.r, P.v, S_th * inv_sp, nx);
         ldj += logf(S_f * inv_sp);
@@ -362,20 +365,20 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
           x0 = (lo + hi) / 2.0f;
           float sn, cs;
           sincosf(x0, &sn, &cs);
-          float Fs = 0.0f;
+          f32x2 Fs2 = 0ull;
           float bufA[32], bufB[32];
           tmem_ld32_async(tm, bufA);
           tmem_ld_wait32(bufA);
 #pragma unroll 1
           for (int j = 0; j < 4; ++j) {
             tmem_ld32_async(tm + 64 * j + 32, bufB);
-            probeN<8>(cs, sn, bufA, Fs);
+            probe_pairs<4>(cs, sn, bufA, Fs2);
             tmem_ld_wait32(bufB);
             if (j < 3) tmem_ld32_async(tm + 64 * j + 64, bufA);
-            probeN<8>(cs, sn, bufB, Fs);
+            probe_pairs<4>(cs, sn, bufB, Fs2);
             if (j < 3) tmem_ld_wait32(bufA);
           }
-          const float fx0 = Fs / S_sp - ys;
+          const float fx0 = hsum(Fs2) / S_sp - ys;
           const float half_w = (hi - lo) / 2.0f;
           if (fx0 < 0.0f) lo = lo + half_w;
           else if (fx0 >= 0.0f) hi = hi - half_w;
@@ -385,15 +388,14 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
         nx[0] = fmaf(P.v[0], sn, P.r[0] * cs);
         nx[1] = fmaf(P.v[1], sn, P.r[1] * cs);
         nx[2] = fmaf(P.v[2], sn, P.r[2] * cs);
-        float Sf = 0.0f;
+        f32x2 Sf2 = 0ull;
 #pragma unroll 1
         for (int q = 0; q < 8; ++q) {
           float prm[32];
           tmem_ld32(tm + 32 * q, prm);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) Sf = fmaf(prm[4 * k + 3], comp_f2(cs, sn, prm[4 * k], prm[4 * k + 1], prm[4 * k + 2]), Sf);
+          jacobian_pairs<4>(cs, sn, prm, Sf2);
         }
-        ldj -= logf(Sf / S_sp);
+        ldj -= logf(hsum(Sf2) / S_sp);
       }
       cross3(nx, y, nz);
       normalize3_fast(nz);
@@ -470,6 +472,12 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
 }
 
 }  // namespace
+
+bool flow_tc_supported(const rnf_flow* f) {
+  for (int i = 0; i < f->model.n_layers; ++i)
+    if (f->layers_host[i].kind == RNF_LAYER_MOBIUS && f->layers_host[i].w_off_tc < 0) return false;
+  return true;
+}
 
 cudaError_t launch_flow_row(const FlowArgs& a, bool inverse, int sm_count, cudaStream_t st) {
   const bool grid_mode = a.G > 0;

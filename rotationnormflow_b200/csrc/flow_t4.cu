@@ -17,6 +17,7 @@
 //     block (c_hi, c_lo) in grid mode (a tile never straddles images); in row mode it is added in the epilogue.
 // One thread owns one rotation (512 threads = 4 tiles x 128 rows): nothing is computed twice, nothing is exchanged.
 // The bisection of Flow.inverse needs its 256 prepared parameters resident per row and stays in flow_row.cu.
+#include "mobius_pair.cuh"
 #include "tc_common.cuh"
 
 namespace rnf {
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
         __syncwarp();
       };
       if (issuer_warp) issue_chunk(0);
-      float S_sp = 0.0f, S_th = 0.0f, S_f = 0.0f;
+      f32x2 S_sp2 = 0ull, S_th2 = 0ull, S_f2 = 0ull;   // packed partial sums (even | odd components)
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         float buf0[16], buf1[16];
@@ -348,10 +349,10 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
         tmem_ld16_async(tm + kColD, buf0);
         tmem_ld16_async(tm + kColD + 16, buf1);
         tmem_ld_wait16(buf0);
-        mixture4<true>(P, zr, zv, buf0, S_sp, S_th, S_f);
+        mixture_pairs<2, true>(P, zr, zv, buf0, S_sp2, S_th2, S_f2);
         tmem_ld16_async(tm + kColD + 32, buf0);
         tmem_ld_wait16(buf1);
-        mixture4<true>(P, zr, zv, buf1, S_sp, S_th, S_f);
+        mixture_pairs<2, true>(P, zr, zv, buf1, S_sp2, S_th2, S_f2);
         tmem_ld16_async(tm + kColD + 48, buf1);
         tmem_ld_wait16(buf0);
         tmem_ld_wait16(buf1);
@@ -359,13 +360,14 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
           hand_over();
           if (issuer_warp) issue_chunk(c + 1);
         }
-        mixture4<true>(P, zr, zv, buf0, S_sp, S_th, S_f);
-        mixture4<true>(P, zr, zv, buf1, S_sp, S_th, S_f);
+        mixture_pairs<2, true>(P, zr, zv, buf0, S_sp2, S_th2, S_f2);
+        mixture_pairs<2, true>(P, zr, zv, buf1, S_sp2, S_th2, S_f2);
       }
       if (issuer_warp) par_w ^= 0xFu;
       if (elected && (atomicAdd(&s_cnt[3], 1) & 3) == 3 && step + 1 < total_steps) load_piece(mob_n1, 3, 0);
       TRACE(18);
       float nx[3], nz[3];
+      const float S_sp = hsum(S_sp2), S_th = hsum(S_th2), S_f = hsum(S_f2);
       const float inv_sp = rcp_nr(S_sp);
       circle_point(P.r, P.v, S_th * inv_sp, nx);
       ldj += logf(S_f * inv_sp);

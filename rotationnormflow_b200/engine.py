@@ -27,7 +27,9 @@ TC_AVAILABLE = True    # csrc/flow_tc.cu: tcgen05 conditioner (forward, inverse 
 TC_WEIGHT_SCALE = 1.0    # fp16 hi/lo weight planes are stored unscaled (biases ride along as a K=16 block, see pack_mobius_tc)
 MOB_TC_FLOATS = (3 * (2 * 8192 + 64 * 32) + (2 * 32768 + 256 * 32) + 1024 + 64 * 32) // 4   # kTcImageBytes / 4 in csrc/tc_common.cuh
 
-_MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC, "tc_row": _cabi.RNF_MLP_TC_ROW, "tc4": _cabi.RNF_MLP_TC4}
+LOG2E = 1.4426950408889634
+
+_MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC, "tc_row": _cabi.RNF_MLP_TC_ROW}
 
 
 def default_mlp_mode() -> str:
@@ -47,6 +49,19 @@ def _last_layer_perm(K: int) -> np.ndarray:
     for c in range(K):
         perm[4 * c] = c
         perm[4 * c + 1: 4 * c + 4] = K + 3 * c + np.arange(3)
+    return perm
+
+
+def _last_layer_perm_pairs(K: int) -> np.ndarray:
+    """Output permutation of fc_last for the tensor-core kernels: components are laid out in pairs (a, b) = (2p, 2p+1),
+    8 columns per pair: (logit_a, logit_b, w_a.x, w_b.x, w_a.y, w_b.y, w_a.z, w_b.z), so that a tcgen05.ld vector delivers
+    the operands of the packed f32x2 arithmetic as aligned register pairs (csrc/mobius_pair.cuh)."""
+    perm = np.empty(4 * K, dtype=np.int64)
+    for c in range(K):
+        base = 8 * (c // 2) + (c % 2)
+        perm[base] = c
+        for q in range(3):
+            perm[base + 2 * (q + 1)] = K + 3 * c + q
     return perm
 
 
@@ -136,10 +151,15 @@ def pack_mobius_tc(cond_sd: dict) -> np.ndarray:
         b = _np(cond_sd[f"layers.{j}.bias"])
         blk = _bias_block(b, W0y, b0) if j == 5 else _bias_block(b)
         parts += [_umma_k_major_sw128(hi).view(np.float32), _umma_k_major_sw128(lo).view(np.float32), blk.view(np.float32)]
-    perm = _last_layer_perm(K_SEGMENTS)
-    hi, lo = _split_fp16(_np(cond_sd["fc_last.weight"])[perm])
+    # fc_last: pair layout; the logit rows carry the factor log2(e) so that the kernels feed them to ex2 directly (the
+    # mixture weights then come out in units of ln 2, a common factor that cancels in every ratio the flow uses)
+    W4, b4 = _np(cond_sd["fc_last.weight"]).copy(), _np(cond_sd["fc_last.bias"]).copy()
+    W4[:K_SEGMENTS] *= np.float32(LOG2E)
+    b4[:K_SEGMENTS] *= np.float32(LOG2E)
+    perm = _last_layer_perm_pairs(K_SEGMENTS)
+    hi, lo = _split_fp16(W4[perm])
     parts += [_umma_k_major_sw128(hi).view(np.float32), _umma_k_major_sw128(lo).view(np.float32),
-              _bias_block(_np(cond_sd["fc_last.bias"])[perm]).view(np.float32)]
+              _bias_block(b4[perm]).view(np.float32)]
     parts.append(np.concatenate([W0y, b0[:, None]], axis=1).astype(np.float32).reshape(-1))
     parts.append(_bias_block(b0, W0y).view(np.float32))
     blk = np.concatenate(parts).astype(np.float32, copy=False)

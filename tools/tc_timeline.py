@@ -12,25 +12,27 @@ cfg, flow = bench.build_flow()
 flow = flow.cuda().eval()
 lib = _cabi.load()
 raw = C.CDLL(_cabi.library_path())
-trace = torch.zeros(2 * 8 * 32, dtype=torch.int64, device="cuda")
+trace = torch.zeros(4 * 8 * 32, dtype=torch.int64, device="cuda")
 raw.rnf_debug_set_trace.argtypes = [C.c_void_p]
 raw.rnf_debug_set_trace(C.c_void_p(trace.data_ptr()))
 G = rgrid.healpix_grid(5)
 feat = torch.relu(torch.randn(1, 2048)).cuda()
 out = flow.grid_log_prob(G, feat, mlp_mode=os.environ.get("RNF_TRACE_MODE", "tc"))
 torch.cuda.synchronize()
-t = trace.cpu().reshape(2, 8, 32)
-names = {0: "start", 1: "turn", 2: "prologue", 3: "bar1", 4: "iss1", 5: "mma1", 6: "epi1", 7: "bar2", 8: "iss2", 9: "mma2", 10: "epi2",
-         11: "bar3", 12: "iss3", 13: "mma3", 14: "epi3", 15: "bar4", 16: "iss4", 17: "mmaA", 18: "mix", 19: "xchg", 20: "end"}
+mode = os.environ.get("RNF_TRACE_MODE", "tc")
+if mode == "tc4":
+    names = {0: "start", 1: "yblk", 2: "iss0", 3: "mma0", 4: "epi0", 5: "iss1", 6: "mma1", 7: "epi1", 8: "iss2", 9: "mma2", 10: "epi2",
+             11: "iss3", 12: "mma3", 13: "epi3", 14: "chunk0", 15: "chunk1", 16: "chunk2", 17: "chunk3", 18: "mix", 19: "end"}
+else:
+    names = {0: "start", 1: "turn", 2: "prologue", 3: "bar1", 4: "iss1", 5: "mma1", 6: "epi1", 7: "bar2", 8: "iss2", 9: "mma2", 10: "epi2",
+             11: "bar3", 12: "iss3", 13: "mma3", 14: "epi3", 15: "bar4", 16: "iss4", 17: "mmaA", 18: "mix", 19: "xchg", 20: "end"}
+n_tiles = 4 if mode == "tc4" else 2
+t = trace.cpu().reshape(-1, 8, 32)[:n_tiles]
 t0 = int(t[t > 0].min())
+last = max(names)
 for s in range(2, 6):
-    for tile in range(2):
+    for tile in range(n_tiles):
         row = t[tile, s]
         base = int(row[0])
-        print(f"step {40+s} tile {tile}: start @{base - t0:7d} | " + " ".join(f"{names[i]}+{int(row[i]) - int(row[i-1])}" for i in range(1, 21)))
-# absolute phase boundaries: chain = [start, iss4], wait = [iss4, mmaA], mixture = [mmaA, mix], tail = [mix, end]
-print("absolute timeline (cycles since first stamp): chain_start, fc_last_issued, mixture_start, mixture_end, layer_end")
-for s in range(2, 6):
-    for tile in range(2):
-        row = t[tile, s]
-        print(f"step {40+s} tile {tile}: " + " ".join(f"{int(row[i]) - t0:7d}" for i in (0, 16, 17, 18, 20)))
+        print(f"step {40+s} tile {tile}: start @{base - t0:7d} | " + " ".join(f"{names[i]}+{int(row[i]) - int(row[i-1])}" for i in range(1, last + 1))
+              + f" | total {int(row[last]) - base}")
