@@ -86,27 +86,44 @@ __device__ __forceinline__ uint32_t pack_h2(__half lo, __half hi) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// Epilogue of one GEMM for 32 of my row's 64 hidden units: accumulator -> (+ c) -> ReLU -> fp16 hi / lo -> A operand in TMEM
-__device__ __forceinline__ void epilogue32(uint32_t tm, int h, const float* cadd) {
-  float acc[32];
-  tmem_ld32(tm + kColD + 32 * h, acc);
-  if (cadd != nullptr) {
+// ReLU + error-compensated fp16 split of two activations (tc_common.cuh: relu_split2); the residual x - hi is one mixed-
+// precision FMA per element (sm_100 FHFMA: f16 * f16 + f32 -> f32, exact here), no unpacking of hi.
+__device__ __forceinline__ void relu_split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  float d0, d1;
+  asm("{\n"
+      ".reg .b16 h0, h1, m1;\n"
+      "mov.b32 {h0, h1}, %2;\n"
+      "mov.b16 m1, 0xBC00;\n"                       // -1.0 in fp16
+      "fma.rn.f32.f16 %0, h0, m1, %3;\n"
+      "fma.rn.f32.f16 %1, h1, m1, %4;\n"
+      "}\n"
+      : "=f"(d0), "=f"(d1)
+      : "r"(hi), "f"(x0), "f"(x1));
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
+}
+
+// Epilogue of one GEMM: my row of the accumulator -> (+ c) -> ReLU -> fp16 hi / lo -> A operand in TMEM (K element 2e in the
+// low half of column e).  The four stores are waited for once.
+__device__ __forceinline__ void epilogue64(uint32_t tm, const float* cadd) {
 #pragma unroll
-    for (int j4 = 0; j4 < 8; ++j4) {
-      const float4 c = __ldg(reinterpret_cast<const float4*>(cadd + 32 * h) + j4);
-      acc[4 * j4] += c.x; acc[4 * j4 + 1] += c.y; acc[4 * j4 + 2] += c.z; acc[4 * j4 + 3] += c.w;
+  for (int h = 0; h < 2; ++h) {
+    float acc[32];
+    tmem_ld32(tm + kColD + 32 * h, acc);
+    if (cadd != nullptr) {
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(cadd + 32 * h) + j4);
+        acc[4 * j4] += c.x; acc[4 * j4 + 1] += c.y; acc[4 * j4 + 2] += c.z; acc[4 * j4 + 3] += c.w;
+      }
     }
-  }
-  float hi[16], lo[16];
+    uint32_t hi[16], lo[16];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    uint32_t uh, ul;
-    relu_split2(acc[2 * e], acc[2 * e + 1], uh, ul);       // K element 2e in the low half, 2e + 1 in the high half
-    hi[e] = __uint_as_float(uh);
-    lo[e] = __uint_as_float(ul);
+    for (int e = 0; e < 16; ++e) relu_split_pair(acc[2 * e], acc[2 * e + 1], hi[e], lo[e]);
+    tmem_st16_nowait(tm + kColAhi + 16 * h, hi);
+    tmem_st16_nowait(tm + kColAlo + 16 * h, lo);
   }
-  tmem_st16(tm + kColAhi + 16 * h, hi);
-  tmem_st16(tm + kColAlo + 16 * h, lo);
+  tmem_st_wait();
 }
 
 template <bool GRID>
@@ -321,8 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
           else if ((atomicAdd(&s_cnt[l - 1], 1) & 3) == 3 && step + 1 < total_steps) load_piece(mob_n1, l - 1, 0);
         }
         const float* ca = (l == 0 || l == 3) ? cadd : nullptr;
-        epilogue32(tm, 0, ca);
-        epilogue32(tm, 1, ca);
+        epilogue64(tm, ca);
         hand_over();
         TRACE(4 + 3 * l);
       }

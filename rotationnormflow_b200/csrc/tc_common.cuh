@@ -154,6 +154,17 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float v[16]) {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// stores without the wait (the caller issues one tmem_st_wait() for a batch)
+__device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const uint32_t u[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]),
+      "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // elect.sync: exactly one lane of a converged warp returns true.  Issuing tcgen05.mma under this predicate (inside a
 // warp-uniform branch) lets ptxas move the operands to uniform registers with one R2UR each; with an ordinary
 // per-thread condition it emits an ELECT / R2UR.BROADCAST / BRA.U.ANY loop per MMA (~15 instructions, ~85 cycles each).

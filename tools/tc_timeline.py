@@ -20,13 +20,13 @@ feat = torch.relu(torch.randn(1, 2048)).cuda()
 out = flow.grid_log_prob(G, feat, mlp_mode=os.environ.get("RNF_TRACE_MODE", "tc"))
 torch.cuda.synchronize()
 mode = os.environ.get("RNF_TRACE_MODE", "tc")
-if mode == "tc4":
+if mode == "tc":
     names = {0: "start", 1: "yblk", 2: "iss0", 3: "mma0", 4: "epi0", 5: "iss1", 6: "mma1", 7: "epi1", 8: "iss2", 9: "mma2", 10: "epi2",
              11: "iss3", 12: "mma3", 13: "epi3", 14: "chunk0", 15: "chunk1", 16: "chunk2", 17: "chunk3", 18: "mix", 19: "end"}
 else:
     names = {0: "start", 1: "turn", 2: "prologue", 3: "bar1", 4: "iss1", 5: "mma1", 6: "epi1", 7: "bar2", 8: "iss2", 9: "mma2", 10: "epi2",
              11: "bar3", 12: "iss3", 13: "mma3", 14: "epi3", 15: "bar4", 16: "iss4", 17: "mmaA", 18: "mix", 19: "xchg", 20: "end"}
-n_tiles = 4 if mode == "tc4" else 2
+n_tiles = 4 if mode == "tc" else 2
 t = trace.cpu().reshape(-1, 8, 32)[:n_tiles]
 t0 = int(t[t > 0].min())
 last = max(names)
