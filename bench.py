@@ -313,7 +313,7 @@ def main():
                    "parallelism": f"grid-sharded x{world}, one all-gather of [B,3] f64"},
         "roofline": {"bound": "tensor", "achieved": ach_tensor, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": ach_tensor / pk["bf16_sustained"], "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
-                     "kernel": "flow_tc_kernel" if mode == "tc" else "flow_v1_kernel", "kernel_ms": kt * 1e3,
+                     "kernel": {"tc": "flow_t4_kernel", "tc_row": "flow_row_kernel"}.get(mode, "flow_v1_kernel"), "kernel_ms": kt * 1e3,
                      "algorithmic_flops_per_rotation": {"tensor_eligible": TENSOR_FLOPS_PER_ROT, "fp32_pipe": FP32_FLOPS_PER_ROT,
                                                         "all": ALL_FLOPS_PER_ROT},
                      "fp32_pipe": {"achieved": (ALL_FLOPS_PER_ROT if mode == "fp32" else FP32_FLOPS_PER_ROT) * rot_per_launch / kt / 1e12,

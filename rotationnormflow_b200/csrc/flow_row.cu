@@ -1,12 +1,22 @@
-// flow_row.cu -- thread-per-rotation variant of the tcgen05 flow kernel (forward, inverse and grid mode), sm_100a.
+// flow_row.cu -- fused flow kernel with the conditioner GEMMs on the 5th-gen tensor cores (tcgen05 + TMEM), two tiles per SM,
+// one thread per rotation: forward, inverse (bisection) and grid mode, sm_100a.
 //
-// Same arithmetic, packed weights, GEMM issue and TMEM formats as flow_tc.cu; different ownership.  flow_tc.cu gives a row
-// to two threads (column halves): both repeat the per-row scalar work (frame, affine layers, new column), meet at a named
-// barrier to exchange three partial sums per layer (once per bisection probe in the inverse), and with the 128-register cap
-// of a 512-thread CTA the mixture loop keeps only ~4 dependency chains in flight per warp.  Here ONE thread owns a rotation:
-// 256 threads per CTA (two 128-rotation tiles, four warps each), up to 255 registers per thread, so the mixture runs eight
-// components at a time stage by stage (eight independent ~200-cycle chains per warp), nothing is computed twice and nothing
-// is exchanged.  Latency hiding comes from instruction-level parallelism instead of extra warps.
+// One CTA (256 threads, one per SM, persistent) works on a PAIR of 128-rotation tiles.  A tile's 128 rows are the 128 TMEM
+// lanes of its accumulator; a row's thread keeps the rotation's 3x3 matrix and running log|det J| in registers across the
+// whole layer stack (flow/flow.py:53-72).  Per Mobius layer (flow/mobiusflow.py:46-125) and tile:
+//   CUDA cores : frame (r, v), first conditioner layer  h0 = W0[:, :3].y + b0 + c_img  (flow/condition.py:25)
+//                -> ReLU -> split into fp16 (hi, lo) -> K-major 128B-swizzled A operand in shared memory
+//   tensor core: D[128 x 64] = bias + A . W^T as a K = 16 bias MMA plus three products  Alo.Whi + Ahi.Wlo + Ahi.Whi  (fp32
+//                accumulate in TMEM; error-compensated split => fp32-level accuracy), three times (layers.1/3/5)
+//   CUDA cores : tcgen05.ld -> ReLU (residual on the last) -> split -> A operand
+//   tensor core: fc_last  D[128 x 256] in two N = 128 chunks, each committed to its own mbarrier
+//   CUDA cores : the 64 mixture components straight out of TMEM, eight at a time in packed f32x2 arithmetic (mobius_pair.cuh).
+// Inverse direction: the prepared parameters of the 64 components go back into the row's own TMEM lane (256 columns) and the
+// 15 bisection probes of BinFind.forward (flow/mobiusflow.py:196-224) stream them from there -- which is why this kernel keeps
+// two tiles per SM; the forward / grid direction has a four-tile kernel (flow_t4.cu) and uses this one as its cross-check.
+// Weights: the host packs, per Mobius layer, the exact shared-memory image (engine.pack_mobius_tc); one cp.async.bulk per
+// piece brings it in, signalled on an mbarrier, and is re-issued for the next layer as soon as both tiles' MMAs that read the
+// piece have completed -- so weight traffic overlaps the mixture math.
 #include "mobius_pair.cuh"
 #include "tc_common.cuh"
 
@@ -322,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           tmem_ld32_async(tm + 64 * j + 32, bufB);
-          __nanosleep(0);                            // scheduler yield (see flow_tc.cu)
+          __nanosleep(0);                            // scheduler yield: lets the other tile's short MLP-chain bursts in (+3 %)
           mixture_pairs<4, !INV>(P, zr, zv, bufA, S_sp2, S_th2, S_f2);
           if (INV) tmem_st32(tm + 64 * j, bufA);
           tmem_ld_wait32(bufB);

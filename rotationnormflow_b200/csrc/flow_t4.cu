@@ -1,7 +1,7 @@
 // flow_t4.cu -- forward / grid flow kernel with FOUR 128-rotation tiles in flight per SM (tcgen05 + TMEM), sm_100a.
 //
-// flow_tc.cu / flow_row.cu keep two tiles per SM: their activations go to the tensor core through 32 KB of shared memory per
-// tile and fc_last needs 256 TMEM columns per tile.  ncu on those kernels: issue slots 58-65 % active, tensor pipe 29 %, the
+// flow_row.cu keeps two tiles per SM: its activations go to the tensor core through 32 KB of shared memory per tile and
+// fc_last needs 256 TMEM columns per tile.  ncu on that kernel: issue slots 58 % active, tensor pipe 29 %, the
 // rest is exposed latency of the dependent GEMM round trips (15 % of the samples sit in the mbarrier wait) -- two tiles are not
 // enough independent work.  This kernel makes a tile small enough for four:
 //   * the A operand (ReLU'd activations, fp16 hi / lo planes) lives in TENSOR MEMORY: tcgen05.mma in its TS form reads row r

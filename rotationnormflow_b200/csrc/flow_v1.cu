@@ -11,7 +11,7 @@
 // registers.  HBM traffic: 36 B in + 40 B out per rotation (grid mode: 36 B per grid rotation per image tile).
 //
 // This is the precision reference of the library (mlp_mode = RNF_MLP_FP32); the tensor-core path lives in
-// flow_tc.cu and is validated against this one and against the CPU oracle.
+// flow_t4.cu / flow_row.cu and is validated against this one and against the CPU oracle.
 #include "mobius_math.cuh"
 #include "rnf_common.cuh"
 

@@ -83,7 +83,7 @@ __device__ __forceinline__ float quat_affine(const float* __restrict__ W, float 
 }
 
 
-// ---- single-SFU-instruction variants used by the tensor-core path (flow_tc.cu) -------------------------------------
+// ---- single-SFU-instruction variants used by the tensor-core kernels (flow_t4.cu, flow_row.cu) -------------------------------------
 // rcp / rsqrt approximations (<= 1 ulp) followed by one Newton step: ~0.5-1 ulp, no IEEE slow path, no branches.
 __device__ __forceinline__ float rcp_nr(float x) {
   float r;

@@ -1,4 +1,4 @@
-// tc_common.cuh -- PTX wrappers shared by the tcgen05 kernels (flow_tc.cu, flow_tc2.cu): mbarrier, TMA bulk copy,
+// tc_common.cuh -- PTX wrappers shared by the tcgen05 kernels (flow_t4.cu, flow_row.cu): mbarrier, TMA bulk copy,
 // tcgen05.mma / commit / ld / st, UMMA descriptors, the 3-product split GEMM issue, and the packed-image constants.
 #pragma once
 #include <cuda_fp16.h>

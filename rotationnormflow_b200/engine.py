@@ -23,7 +23,7 @@ AFF_FLOATS = 40
 AFF_INV = 20
 CAFF_FLOATS = 64 + 3 * (64 * 64 + 64) + 16 * 64 + 16
 
-TC_AVAILABLE = True    # csrc/flow_tc.cu: tcgen05 conditioner (forward, inverse and grid mode)
+TC_AVAILABLE = True    # csrc/flow_t4.cu (forward, grid) + csrc/flow_row.cu (inverse): tcgen05 conditioner
 TC_WEIGHT_SCALE = 1.0    # fp16 hi/lo weight planes are stored unscaled (biases ride along as a K=16 block, see pack_mobius_tc)
 MOB_TC_FLOATS = (3 * (2 * 8192 + 64 * 32) + (2 * 32768 + 256 * 32) + 1024 + 64 * 32) // 4   # kTcImageBytes / 4 in csrc/tc_common.cuh
 
@@ -119,7 +119,7 @@ def _bias_block(b: np.ndarray, W0: np.ndarray | None = None, b0: np.ndarray | No
         0, 1   : (b_hi, b_lo)                                  -- bias of the layer
         2 .. 10: (W0hi[n,:3], W0hi[n,:3], W0lo[n,:3])           -- fc_first columns acting on the conditioning column y
         b0_slot, b0_slot + 1 : (b0_hi, b0_lo)                   -- fc_first bias (for the residual x0 + x3)
-    The kernels multiply it by a per-rotation [128 x 16] A block.  csrc/flow_tc.cu / flow_row.cu use a constant block with
+    The kernels multiply it by a per-rotation [128 x 16] A block.  csrc/flow_row.cu uses a constant block with
     ones in slots 0, 1 (bias only); csrc/flow_t4.cu uses (1, 1, y_hi, y_lo, y_hi, 1, 1, 0, 0, 0), which makes the tensor core
     evaluate fc_first (flow/condition.py:25) and re-create x0 inside the last hidden GEMM (flow/condition.py:29)."""
     N = b.shape[0]
@@ -141,7 +141,7 @@ def _bias_block(b: np.ndarray, W0: np.ndarray | None = None, b0: np.ndarray | No
 def pack_mobius_tc(cond_sd: dict) -> np.ndarray:
     """Tensor-core image of one Mobius conditioner = the exact shared-memory pieces of the tcgen05 kernels:
     3 x [hi 64x64 | lo 64x64 fp16 SW128 | bias block 64x16] | [hi 256x64 | lo 256x64 SW128 | bias block 256x16]
-    | aux: first[64][4] fp32 (flow_tc / flow_row: fc_first on the CUDA cores), fc_first block 64x16 (flow_t4: on the tensor core)
+    | aux: first[64][4] fp32 (flow_row: fc_first on the CUDA cores), fc_first block 64x16 (flow_t4: on the tensor core)
     returned as float32 words (MOB_TC_FLOATS of them).  The block of the last hidden layer also carries fc_first (residual)."""
     W0, b0 = _np(cond_sd["fc_first.weight"]), _np(cond_sd["fc_first.bias"])
     W0y = np.ascontiguousarray(W0[:, :3])

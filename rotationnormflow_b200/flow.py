@@ -8,7 +8,7 @@ Same public surface, same constructor semantics, same ``state_dict`` keys -- che
     Flow.inverse(rotation, feature=None, draw=False)                     flow/flow.py:74-92
     layer(rotation, permute, feature) / layer.inverse(...)               per-layer protocol of flow/*.py
 
-but every call runs as ONE fused CUDA kernel over the whole layer stack (csrc/flow_v1.cu, csrc/flow_tc.cu)
+but every call runs as ONE fused CUDA kernel over the whole layer stack (csrc/flow_v1.cu, csrc/flow_t4.cu, csrc/flow_row.cu)
 instead of ~6.5 k (forward) / ~22 k (inverse) ATen launches.  The modules below only hold parameters; they
 contain no per-rotation PyTorch arithmetic and there is no CPU path: tensors must live on a B200.
 

@@ -78,3 +78,11 @@ def test_softplus_series_branch():
     src = open(os.path.join(ROOT, "rotationnormflow_b200", "csrc", "mobius_fast.cuh")).read()
     m = re.search(r"small = e \* fmaf\(e, (-?[0-9.]+)f, ([0-9.]+)f\)", src)
     assert abs(float(m.group(2)) - 1 / np.log(2)) < 1e-12 and abs(float(m.group(1)) + 0.5 / np.log(2)) < 1e-12
+
+
+def test_packed_atan_uses_the_same_polynomial():
+    """mobius_pair.cuh evaluates atan for two components per instruction with the coefficients of atan2_wrapped_fast."""
+    src = open(os.path.join(ROOT, "rotationnormflow_b200", "csrc", "mobius_pair.cuh")).read()
+    body = src[src.index("f32x2 atan_unit2"):src.index("octant_ratio")]
+    packed = [float(v) for v in re.findall(r"bc\((-?[0-9.e-]+)f\)", body)]
+    assert packed == _coeffs()[::-1]

@@ -97,6 +97,74 @@ def test_mobius_packing_is_the_reference_mlp():
         assert np.abs(out[4 * c + 1: 4 * c + 4] - ref[K + 3 * c: K + 3 * c + 3]).max() < 1e-12
 
 
+def _unswizzle_sw128(words: np.ndarray, N: int) -> np.ndarray:
+    """Inverse of engine._umma_k_major_sw128: float32 words of a [N x 64] fp16 K-major SWIZZLE_128B tile -> [N, 64] float64."""
+    h = words.view(np.float16)
+    n = np.arange(N)[:, None]
+    k = np.arange(64)[None, :]
+    off = (n // 8) * 1024 + (n % 8) * 128 + (((k // 8) ^ (n % 8)) * 16) + (k % 8) * 2
+    return h[off // 2].astype(np.float64)
+
+
+def _unblock(words: np.ndarray, N: int) -> np.ndarray:
+    """[N x 16] no-swizzle K-major block (engine._bias_block) -> [N, 16] float64 slot values."""
+    h = words.view(np.float16)
+    n = np.arange(N)[:, None]
+    k = np.arange(16)[None, :]
+    off = (n // 8) * 256 + (k // 8) * 128 + (n % 8) * 16 + (k % 8) * 2
+    return h[off // 2].astype(np.float64)
+
+
+def test_tensor_core_image_is_the_reference_mlp():
+    """Emulates what csrc/flow_t4.cu does with the packed image (engine.pack_mobius_tc): every GEMM = Y block x layer block
+    (bias, fc_first on y, residual x0) + activations x (hi + lo planes); fc_last in the pair column layout with the logits
+    scaled by log2(e).  Checked against the float64 oracle conditioner (flow/condition.py:24-30)."""
+    g = golden("s_symsol")
+    sd = {k: v.double() for k, v in g.state_dict().items()}
+    pre = "layers.1.conditioner."
+    sub = {k[len(pre):]: v for k, v in g.state_dict().items() if k.startswith(pre)}
+    F = orc.feature_dim_of(g.cfg)
+    img = engine.pack_mobius_tc(sub)
+    assert img.size == engine.MOB_TC_FLOATS
+    _, wf = engine.pack_mobius(sub, F)
+    rng = np.random.default_rng(3)
+    y = rng.standard_normal(3)
+    y /= np.linalg.norm(y)
+    feat = rng.standard_normal(F)
+    c = wf.astype(np.float64) @ feat
+    yh = y.astype(np.float16).astype(np.float64)
+    yl = (y - yh).astype(np.float16).astype(np.float64)
+    Y = np.concatenate([[1, 1], yh, yl, yh, [1, 1], [0, 0, 0]])        # the kernel's per-rotation block
+    o = 0
+    hid = []
+    for _ in range(3):
+        W = _unswizzle_sw128(img[o:o + 2048], 64) + _unswizzle_sw128(img[o + 2048:o + 4096], 64)
+        blk = _unblock(img[o + 4096:o + 4608], 64)
+        hid.append((W, blk))
+        o += 4608
+    W4 = _unswizzle_sw128(img[o:o + 8192], 256) + _unswizzle_sw128(img[o + 8192:o + 16384], 256)
+    blk4 = _unblock(img[o + 16384:o + 18432], 256)
+    o += 18432
+    blk0 = _unblock(img[o + 256:o + 256 + 512], 64)
+    assert o + 256 + 512 == img.size
+    x0 = blk0 @ Y + c
+    x = np.maximum(x0, 0)
+    for l, (W, blk) in enumerate(hid):
+        x = W @ x + blk @ Y + (c if l == 2 else 0)                        # last hidden block re-creates x0 (residual)
+        x = np.maximum(x, 0)
+    out = W4 @ x + blk4 @ Y
+    ref = orc.conditioner(sd, pre, torch.from_numpy(np.concatenate([y, feat]))[None])[0].numpy()
+    K = 64
+    scale = np.abs(ref).max()
+    for comp in (0, 1, 2, 17, 62, 63):
+        base = 8 * (comp // 2) + (comp % 2)
+        assert abs(out[base] - ref[comp] * engine.LOG2E) < 2e-6 * scale
+        got_w = out[[base + 2, base + 4, base + 6]]
+        assert np.abs(got_w - ref[K + 3 * comp: K + 3 * comp + 3]).max() < 2e-6 * scale
+    perm = engine._last_layer_perm_pairs(K)
+    assert sorted(perm.tolist()) == list(range(4 * K))
+
+
 def test_affine_packing():
     W = torch.eye(4) + 0.1 * torch.randn(4, 4, generator=torch.Generator().manual_seed(0))
     blk = engine.pack_affine_matrix(W[None], is_rot=False)
