@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RNF_ABI_VERSION 4
+#define RNF_ABI_VERSION 5
 
 /* error codes */
 #define RNF_OK 0

@@ -11,7 +11,7 @@ import threading
 
 from . import build as _build
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 RNF_LAYER_MOBIUS = 0
 RNF_LAYER_AFFINE = 1

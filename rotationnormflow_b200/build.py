@@ -27,10 +27,10 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    names = sorted(os.listdir(CSRC)) + ["../../include/rnf_abi.h"]
+    names = [n for n in sorted(os.listdir(CSRC)) if not n.startswith(".")] + ["../../include/rnf_abi.h"]
     for n in names:
         p = os.path.join(CSRC, n)
-        if os.path.isfile(p) and not n.startswith("."):
+        if os.path.isfile(p):
             h.update(n.encode())
             with open(p, "rb") as f:
                 h.update(f.read())
