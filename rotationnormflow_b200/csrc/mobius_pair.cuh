@@ -45,6 +45,8 @@ __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// sign flip of both halves: a bit operation that ptxas folds into the negate modifier of the consuming FFMA2 / FADD2
+__device__ __forceinline__ f32x2 neg2(f32x2 a) { return a ^ 0x8000000080000000ull; }
 __device__ __forceinline__ float hsum(f32x2 v) {
   float lo, hi;
   upk(v, lo, hi);
@@ -81,7 +83,7 @@ template <int NP, bool FWD>
 __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv, float* raw, f32x2& S_sp, f32x2& S_th, f32x2& S_f) {
   f32x2 sp[NP], nal[NP], nbe[NP], omw[NP];
   {
-    f32x2 t[NP], e[NP], a[NP], b[NP], rt[NP], big[NP], small[NP], ns[NP];
+    f32x2 t[NP], e[NP], a[NP], b[NP], n2[NP], rt[NP], big[NP], small[NP], ns[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       t[j] = pk(raw[8 * j], raw[8 * j + 1]);
@@ -92,8 +94,8 @@ __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv
       const f32x2 wx = pk(raw[8 * j + 2], raw[8 * j + 3]), wy = pk(raw[8 * j + 4], raw[8 * j + 5]), wz = pk(raw[8 * j + 6], raw[8 * j + 7]);
       a[j] = fma2(wz, bc(P.r[2]), fma2(wy, bc(P.r[1]), mul2(wx, bc(P.r[0]))));
       b[j] = fma2(wz, bc(P.v[2]), fma2(wy, bc(P.v[1]), mul2(wx, bc(P.v[0]))));
-      const f32x2 n2 = fma2(b[j], b[j], mul2(a[j], a[j]));
-      RNF_MAP2(rt[j], n2, sqrt_approx);
+      n2[j] = fma2(b[j], b[j], mul2(a[j], a[j]));
+      RNF_MAP2(rt[j], n2[j], sqrt_approx);
     }
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
@@ -116,15 +118,16 @@ __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv
       sp[j] = pk(tl > 28.853900817779268f ? tl : vl, th > 28.853900817779268f ? th : vh);
       nal[j] = mul2(ns[j], a[j]);
       nbe[j] = mul2(ns[j], b[j]);
-      const f32x2 m = fma2(nal[j], nal[j], mul2(nbe[j], nbe[j]));
-      omw[j] = fma2(m, bc(-1.0f), bc(1.0f));
+      omw[j] = fma2(neg2(mul2(ns[j], ns[j])), n2[j], bc(1.0f));        // 1 - |w'|^2 = 1 - (0.7 / (1 + |w|))^2 |w|^2
     }
   }
   if (FWD) {
     f32x2 f[NP], hr[NP], hv[NP], q[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-      const f32x2 dr = add2(nal[j], bc(zr)), dv = add2(nbe[j], bc(zv));
+      // forward direction: the evaluation point is the moving column itself, z = -|x| r exactly (v is orthogonal to x), so
+      // zv = 0 and z - w' has the in-plane components (zr - alpha', -beta')
+      const f32x2 dr = add2(nal[j], bc(zr)), dv = nbe[j];
       const f32x2 dd = fma2(dv, dv, mul2(dr, dr));
       f32x2 rc;
       RNF_MAP2(rc, dd, rcp_approx);
