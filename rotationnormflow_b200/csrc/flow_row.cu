@@ -361,8 +361,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
       if (!INV) {
         const float S_th = hsum(S_th2), S_f = hsum(S_f2);
         const float inv_sp = rcp_nr(S_sp);
-        circle_point(P.r, P.v, S_th * inv_sp, nx);
-        ldj += logf(S_f * inv_sp);
+        circle_point_fast(P.r, P.v, S_th * inv_sp, nx);
+        ldj += log_fast(S_f * inv_sp);
       } else {
         // target angle of the given column in its own frame (flow/mobiusflow.py:157-167); ~pi by construction
         float ys = atan2f(zv, zr);
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
         for (int it = 0; it < 15; ++it) {
           x0 = (lo + hi) / 2.0f;
           float sn, cs;
-          sincosf(x0, &sn, &cs);
+          sincos_2pi(x0, sn, cs);
           f32x2 Fs2 = 0ull;
           float bufA[32], bufB[32];
           tmem_ld32_async(tm, bufA);
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
           else if (fx0 >= 0.0f) hi = hi - half_w;
         }
         float sn, cs;
-        sincosf(x0, &sn, &cs);
+        sincos_2pi(x0, sn, cs);
         nx[0] = fmaf(P.v[0], sn, P.r[0] * cs);
         nx[1] = fmaf(P.v[1], sn, P.r[1] * cs);
         nx[2] = fmaf(P.v[2], sn, P.r[2] * cs);
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
           tmem_ld32(tm + 32 * q, prm);
           jacobian_pairs<4>(cs, sn, prm, Sf2);
         }
-        ldj -= logf(hsum(Sf2) / S_sp);
+        ldj -= log_fast(hsum(Sf2) / S_sp);
       }
       cross3(nx, y, nz);
       normalize3_fast(nz);

@@ -39,6 +39,31 @@ __device__ __forceinline__ float lg2_approx(float x) {
   return r;
 }
 
+// log(x) through the SFU: lg2.approx (absolute error <= 2^-22 on the result) times ln 2.  Used for the log-det terms, which
+// are O(1) per layer and checked at 1e-4 relative after 42-49 layers.
+__device__ __forceinline__ float log_fast(float x) { return 0.6931471805599453f * lg2_approx(x); }
+
+// sin and cos of t in [0, 2 pi] (mixture angles and bisection probes never leave that range): quadrant by the magic-number
+// round of t * 2/pi, two-constant Cody-Waite reduction to [-pi/4, pi/4], degree-7 / degree-8 minimax polynomials (the
+// classic single-precision kernels).  Max abs error 9e-8 (tests/test_fastmath.py); ~20 instructions, no slow path.
+__device__ __forceinline__ void sincos_2pi(float t, float& sn, float& cs) {
+  const float kbig = fmaf(t, 0.63661977236758134f, 12582912.0f);        // 1.5 * 2^23: the integer lands in the low mantissa bits
+  const int q = __float_as_int(kbig);
+  const float kf = kbig - 12582912.0f;
+  float r = fmaf(kf, -1.5707963705062866f, t);
+  r = fmaf(kf, 4.371138828673793e-08f, r);
+  const float z = r * r;
+  float ps = fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f);
+  ps = fmaf(ps, z, -1.6666654611e-1f);
+  const float s = fmaf(ps * z, r, r);
+  float pc = fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f);
+  pc = fmaf(pc, z, 4.166664568298827e-2f);
+  const float c = fmaf(pc * z, z, fmaf(-0.5f, z, 1.0f));
+  const float a = (q & 1) ? c : s, b = (q & 1) ? s : c;                  // odd quadrant: sin <-> cos
+  sn = (q & 2) ? -a : a;
+  cs = ((q + 1) & 2) ? -b : b;
+}
+
 // Mixture weight of a component, in units of ln 2:  softplus(a) / ln 2 = log2(1 + 2^t),  t = a log2(e).
 // theta' = sum_k sp_k theta_k / sum_k sp_k and log sum_k sp_k f_k / sum_k sp_k are ratios, so the common factor ln 2
 // never has to be applied.  torch's softplus is the identity above a = 20 (threshold), i.e. t above 20 log2(e); for
@@ -99,6 +124,15 @@ __device__ __forceinline__ float atan2_left_half_plane(float y, float x) {
   p = fmaf(p, q, q);                                  // atan(q), q in [0,1]
   p = ay > ax ? 1.5707963267948966f - p : p;          // atan(|y| / |x|)
   return y < 0.0f ? kPi + p : kPi - p;
+}
+
+// point on the circle: z = r cos(t) + v sin(t), t in [0, 2 pi]            (flow/mobiusflow.py:102,169,231)
+__device__ __forceinline__ void circle_point_fast(const float r[3], const float v[3], float t, float z[3]) {
+  float s, c;
+  sincos_2pi(t, s, c);
+  z[0] = fmaf(v[0], s, r[0] * c);
+  z[1] = fmaf(v[1], s, r[1] * c);
+  z[2] = fmaf(v[2], s, r[2] * c);
 }
 
 // Per-layer constants of a row: frame (r, v).

@@ -137,7 +137,9 @@ __device__ __forceinline__ float quat_affine_fast(const float* __restrict__ W, f
   R[6] = fmaf(si, k, -sj * r);
   R[7] = fmaf(sj, k, si * r);
   R[8] = 1.0f - fmaf(si, i, sj * j);
-  return 0.5f * logf(pp * rcp_nr(4.0f * am));
+  float l2;                                          // log through the SFU (lg2.approx: absolute error <= 2^-22)
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(pp * rcp_nr(4.0f * am)));
+  return 0.34657359027997264f * l2;                  // 0.5 ln 2
 }
 
 __host__ __device__ inline float det3f(float a00, float a01, float a02, float a10, float a11, float a12, float a20,

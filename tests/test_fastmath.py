@@ -86,3 +86,35 @@ def test_packed_atan_uses_the_same_polynomial():
     body = src[src.index("f32x2 atan_unit2"):src.index("octant_ratio")]
     packed = [float(v) for v in re.findall(r"bc\((-?[0-9.e-]+)f\)", body)]
     assert packed == _coeffs()[::-1]
+
+
+def test_sincos_2pi_accuracy():
+    """Float32 emulation of sincos_2pi (mobius_fast.cuh) over [0, 2 pi] with the constants read back from the header."""
+    src = open(os.path.join(ROOT, "rotationnormflow_b200", "csrc", "mobius_fast.cuh")).read()
+    body = src[src.index("void sincos_2pi"):src.index("// Mixture weight of a component")]
+    num = r"(-?[0-9.]+(?:e-?[0-9]+)?)f"
+    two_over_pi, magic = map(float, re.search(r"fmaf\(t, %s, %s\)" % (num, num), body).groups())
+    hi = float(re.search(r"fmaf\(kf, %s, t\)" % num, body).group(1))
+    lo = float(re.search(r"fmaf\(kf, %s, r\)" % num, body).group(1))
+    s3, s2 = map(float, re.search(r"ps = fmaf\(%s, z, %s\)" % (num, num), body).groups())
+    s1 = float(re.search(r"ps = fmaf\(ps, z, %s\)" % num, body).group(1))
+    c3, c2 = map(float, re.search(r"pc = fmaf\(%s, z, %s\)" % (num, num), body).groups())
+    c1 = float(re.search(r"pc = fmaf\(pc, z, %s\)" % num, body).group(1))
+    assert magic == 12582912.0 and abs(two_over_pi - 2 / np.pi) < 1e-9 and abs(-hi - lo - np.pi / 2) < 1e-14
+    f32 = lambda x: np.asarray(x).astype(np.float32)
+    t = np.linspace(0, 2 * np.pi, 1_000_001).astype(np.float32)
+    kf = f32(np.rint(t.astype(np.float64) * np.float32(two_over_pi)))
+    r = f32(t.astype(np.float64) + kf.astype(np.float64) * np.float64(np.float32(hi)))
+    r = f32(r.astype(np.float64) + kf.astype(np.float64) * np.float64(np.float32(lo)))
+    z = f32(r * r)
+    ps = f32(_fma32(f32(np.full_like(z, s3)), z, np.float32(s2)))
+    ps = _fma32(ps, z, np.float32(s1))
+    sn = f32(f32(ps * z).astype(np.float64) * r + r)
+    pc = _fma32(f32(np.full_like(z, c3)), z, np.float32(c2))
+    pc = _fma32(pc, z, np.float32(c1))
+    cs = f32(f32(pc * z).astype(np.float64) * z + f32(np.float32(1) - np.float32(0.5) * z))
+    q = kf.astype(np.int64) & 3
+    S = np.where(q == 0, sn, np.where(q == 1, cs, np.where(q == 2, -sn, -cs)))
+    C = np.where(q == 0, cs, np.where(q == 1, -sn, np.where(q == 2, -cs, sn)))
+    assert np.abs(S - np.sin(t.astype(np.float64))).max() < 1.2e-7
+    assert np.abs(C - np.cos(t.astype(np.float64))).max() < 1.2e-7
