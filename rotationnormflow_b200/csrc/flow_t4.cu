@@ -32,7 +32,13 @@ namespace {
 #define TRACE(i) do { } while (0)
 #endif
 
-constexpr int kTiles = 4;
+#ifndef RNF_T4_TILES
+#define RNF_T4_TILES 4           // tiles in flight per SM (4 = TMEM and register-file ceiling at 128 registers per thread)
+#endif
+#ifndef RNF_T4_NP
+#define RNF_T4_NP 2              // mixture pairs evaluated together
+#endif
+constexpr int kTiles = RNF_T4_TILES;
 constexpr int kThreads = kTiles * 128;
 constexpr int kRows = 128;
 
@@ -45,12 +51,12 @@ constexpr int kOffC = kOffY + kTiles * 4096;              // [tile] per-image bl
 constexpr int kOffRed = kOffC + kTiles * 2048;            // [tile] reduction scratch
 constexpr int kOffBar = kOffRed + kTiles * 128;
 constexpr int kOffMisc = kOffBar + 8 * 16;
-constexpr int kSmemBytes = kOffMisc + 32 + 64 * 8;
+constexpr int kSmemBytes = kOffMisc + 64 + 64 * 8;
 constexpr int kSmemAlloc = kSmemBytes + 1024;
 static_assert(kOffLastW % 1024 == 0 && kW1Bytes % 1024 == 0, "UMMA SW128 tiles need 1024 B alignment");
 static_assert(kOffY % 16 == 0 && kOffC % 16 == 0 && kOffAux % 16 == 0, "no-swizzle blocks need 16 B alignment");
 
-enum { BAR_W_FULL = 0 /* W1,W2,W3,W4 */, BAR_AUX_FULL = 4 /* [2] */, BAR_MMA = 6 /* [tile] */, BAR_COUNT = 10 };
+enum { BAR_W_FULL = 0 /* W1,W2,W3,W4 */, BAR_AUX_FULL = 4 /* [2] */, BAR_MMA = 6 /* [tile] */, BAR_COUNT = 6 + RNF_T4_TILES };
 
 // TMEM columns of a tile
 constexpr uint32_t kColAhi = 0, kColAlo = 32, kColD = 64, kColsPerTile = 128;
@@ -140,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
 
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kOffMisc);
   int* s_cnt = reinterpret_cast<int*>(smem + kOffMisc + 4);                // tiles done with: [0..2] W1..W3, [3] W4, [4 + buf] aux
-  long long* s_moff = reinterpret_cast<long long*>(smem + kOffMisc + 32);
+  long long* s_moff = reinterpret_cast<long long*>(smem + kOffMisc + 64);
 
   int n_mob = 0;
   for (int i = 0; i < a.n_layers; ++i)
@@ -171,7 +177,9 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
   const int64_t my_items = blockIdx.x < n_groups ? (n_groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
   const int64_t total_steps = my_items * n_mob;
   const uint8_t* wbytes = reinterpret_cast<const uint8_t*>(a.weights);
-  auto load_piece = [&](int mob_idx, int piece, int abuf) {   // piece 0..2 = W1..W3, 3 = W4, 4 = aux (into buffer abuf)
+  // piece 0..2 = W1..W3, 3 = W4, 4 = aux (into buffer abuf): one bulk copy each, signalled on the piece's mbarrier.
+  // A piece is refilled for the next layer as soon as ALL tiles' MMAs that read it are done.
+  auto load_piece = [&](int mob_idx, int piece, int abuf) {
     const uint8_t* src = wbytes + s_moff[mob_idx] * 4;
     uint32_t dst, bytes, bar;
     if (piece < 3) { src += piece * kW1Bytes; dst = kOffW + piece * kW1Bytes; bytes = kW1Bytes; bar = BAR_W_FULL + piece; }
@@ -312,8 +320,10 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
 #pragma unroll 1
       for (int l = 0; l < 4; ++l) {
         if (issuer_warp) {
+          TRACE(20 + 2 * l);                          // 20 .. 29: time spent waiting for the weight pieces
           if (l == 0) mbar_wait(bars + 8 * (BAR_AUX_FULL + abuf), (uint32_t)((step >> 1) & 1));
           else mbar_wait(bars + 8 * (BAR_W_FULL + l - 1), (par_w >> (l - 1)) & 1u);
+          TRACE(21 + 2 * l);
           tc_fence_after();
           if (elect_one_sync()) {
             const uint32_t d = tm_tile + kColD;
@@ -334,8 +344,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
         TRACE(3 + 3 * l);
         // a piece is dead once ALL tiles' GEMM that reads it has completed: the last tile to get here refills it
         if (elected) {
-          if (l == 0) { if ((atomicAdd(&s_cnt[4 + abuf], 1) & 3) == 3 && step + 2 < total_steps) load_piece(mob_n2, 4, abuf); }
-          else if ((atomicAdd(&s_cnt[l - 1], 1) & 3) == 3 && step + 1 < total_steps) load_piece(mob_n1, l - 1, 0);
+          if (l == 0) { if ((atomicAdd(&s_cnt[4 + abuf], 1) % kTiles) == kTiles - 1 && step + 2 < total_steps) load_piece(mob_n2, 4, abuf); }
+          else if ((atomicAdd(&s_cnt[l - 1], 1) % kTiles) == kTiles - 1 && step + 1 < total_steps) load_piece(mob_n1, l - 1, 0);
         }
         const float* ca = (l == 0 || l == 3) ? cadd : nullptr;
         epilogue64(tm, ca);
@@ -344,7 +354,11 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
       }
       // ---- fc_last in four N = 64 chunks through the single accumulator; 16 mixture components per chunk ----
       auto issue_chunk = [&](int c) {               // issuing warp only, right after the hand-over barrier
-        if (c == 0) mbar_wait(bars + 8 * (BAR_W_FULL + 3), (par_w >> 3) & 1u);
+        if (c == 0) {
+          TRACE(28);
+          mbar_wait(bars + 8 * (BAR_W_FULL + 3), (par_w >> 3) & 1u);
+          TRACE(29);
+        }
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t d = tm_tile + kColD;
@@ -357,11 +371,31 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
       };
       if (issuer_warp) issue_chunk(0);
       f32x2 S_sp2 = 0ull, S_th2 = 0ull, S_f2 = 0ull;   // packed partial sums (even | odd components)
+      // W4 is dead the moment the last chunk's MMAs have completed (not after the arithmetic on it): the last tile to see that
+      // refills it.  (Refilling W4 chunk by chunk removes the leaders' remaining wait for it but lets three tiles fall into
+      // lock step: 222 M instead of 238 M rot/s -- the coupling through this one piece keeps the tiles in two anti-phase pairs.)
+#define W4_DONE() do { if (c == 3 && elected && (atomicAdd(&s_cnt[3], 1) % kTiles) == kTiles - 1 && step + 1 < total_steps) load_piece(mob_n1, 3, 0); } while (0)
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
+#if RNF_T4_NP == 4
+        float buf[32];
+        wait_mma();
+        TRACE(14 + c);
+        W4_DONE();
+        tmem_ld32(tm + kColD, buf);
+        mixture_pairs<4, true>(P, zr, zv, buf, S_sp2, S_th2, S_f2);
+        tmem_ld32(tm + kColD + 32, buf);
+        if (c < 3) {                                  // accumulator drained: the next chunk runs under the math below
+          hand_over();
+          if (issuer_warp) issue_chunk(c + 1);
+        }
+        mixture_pairs<4, true>(P, zr, zv, buf, S_sp2, S_th2, S_f2);
+      }
+#else
         float buf0[16], buf1[16];
         wait_mma();
         TRACE(14 + c);
+        W4_DONE();
         tmem_ld16_async(tm + kColD, buf0);
         tmem_ld16_async(tm + kColD + 16, buf1);
         tmem_ld_wait16(buf0);
@@ -379,8 +413,9 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
         mixture_pairs<2, true>(P, zr, zv, buf0, S_sp2, S_th2, S_f2);
         mixture_pairs<2, true>(P, zr, zv, buf1, S_sp2, S_th2, S_f2);
       }
+#endif
+#undef W4_DONE
       if (issuer_warp) par_w ^= 0xFu;
-      if (elected && (atomicAdd(&s_cnt[3], 1) & 3) == 3 && step + 1 < total_steps) load_piece(mob_n1, 3, 0);
       TRACE(18);
       float nx[3], nz[3];
       const float S_sp = hsum(S_sp2), S_th = hsum(S_th2), S_f = hsum(S_f2);

@@ -54,26 +54,21 @@ __device__ __forceinline__ float hsum(f32x2 v) {
 }
 #define RNF_MAP2(out, in, fn) do { float l_, h_; upk(in, l_, h_); out = pk(fn(l_), fn(h_)); } while (0)
 
-// atan(q) for a pair, q in [0, 1]: the degree-8 minimax polynomial of atan2_wrapped_fast (same coefficients, Horner in q^2)
-__device__ __forceinline__ f32x2 atan_unit2(f32x2 q) {
-  const f32x2 s = mul2(q, q);
-  f32x2 p = bc(-0.0024470302741974592f);
-  p = fma2(p, s, bc(0.013750280253589153f));
-  p = fma2(p, s, bc(-0.03627016767859459f));
-  p = fma2(p, s, bc(0.06284360587596893f));
-  p = fma2(p, s, bc(-0.08673170208930969f));
-  p = fma2(p, s, bc(0.11037994176149368f));
-  p = fma2(p, s, bc(-0.14279110729694366f));
-  p = fma2(p, s, bc(0.1999976634979248f));
-  p = fma2(p, s, bc(-0.3333333134651184f));
-  return fma2(mul2(p, s), q, q);
-}
-
-// min(|y|,|x|) / max(|y|,|x|) of one component (scalar: FMNMX x2, MUFU.RCP, FMUL is done packed by the caller)
-__device__ __forceinline__ void octant_ratio(float y, float x, float& mn, float& rmx) {
-  const float ay = fabsf(y), ax = fabsf(x);
-  mn = fminf(ay, ax);
-  rmx = rcp_approx(fmaxf(ay, ax));
+// Angle of a UNIT vector from its nearer axis, for a pair: asin(m) with m = min(|h.r|, |h.v|) in [0, 1/sqrt 2].  The Mobius map
+// sends the unit circle to itself, so |h| = 1 (to fp32 rounding) and atan(min / max) = asin(min): no reciprocal on the SFU --
+// the XU pipe (8 cycles per warp instruction, tools/mufu_rate.cu) is the tightest unit of the mixture -- and a shorter
+// polynomial: asin(m) = m + m s P(s), s = m^2, P of degree 6 (minimax fit, max abs error 4.4e-8 in fp32 Horner form,
+// tests/test_fastmath.py).
+__device__ __forceinline__ f32x2 asin_unit2(f32x2 m) {
+  const f32x2 s = mul2(m, m);
+  f32x2 p = bc(0.12371734529733658f);
+  p = fma2(p, s, bc(-0.11529727280139923f));
+  p = fma2(p, s, bc(0.09339626878499985f));
+  p = fma2(p, s, bc(0.01043224148452282f));
+  p = fma2(p, s, bc(0.04762402921915054f));
+  p = fma2(p, s, bc(0.07478351145982742f));
+  p = fma2(p, s, bc(0.16667234897613525f));
+  return fma2(mul2(p, s), m, m);
 }
 
 // NP pairs of mixture components, stage by stage.  raw[8 NP]: accumulator columns in the pair layout above.
@@ -122,7 +117,7 @@ __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv
     }
   }
   if (FWD) {
-    f32x2 f[NP], hr[NP], hv[NP], q[NP];
+    f32x2 f[NP], hr[NP], hv[NP], mn[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       // forward direction: the evaluation point is the moving column itself, z = -|x| r exactly (v is orthogonal to x), so
@@ -134,19 +129,17 @@ __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv
       f[j] = mul2(omw[j], rc);
       hr[j] = fma2(f[j], dr, nal[j]);
       hv[j] = fma2(f[j], dv, nbe[j]);
-      float hrl, hrh, hvl, hvh, mnl, mnh, rl, rh;
+      float hrl, hrh, hvl, hvh;
       upk(hr[j], hrl, hrh);
       upk(hv[j], hvl, hvh);
-      octant_ratio(hvl, hrl, mnl, rl);
-      octant_ratio(hvh, hrh, mnh, rh);
-      q[j] = mul2(pk(mnl, mnh), pk(rl, rh));
+      mn[j] = pk(fminf(fabsf(hvl), fabsf(hrl)), fminf(fabsf(hvh), fabsf(hrh)));
     }
     f32x2 at[NP];
 #pragma unroll
-    for (int j = 0; j < NP; ++j) at[j] = atan_unit2(q[j]);
+    for (int j = 0; j < NP; ++j) at[j] = asin_unit2(mn[j]);
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-      // atan(|hv| / |hr|); hr < 0 always in the forward direction, so theta = pi - sign(hv) * that   (atan2_left_half_plane)
+      // angle of h from the negative r axis; hr < 0 always in the forward direction, so theta = pi - sign(hv) * that
       const f32x2 alt = fma2(at[j], bc(-1.0f), bc(1.5707963267948966f));
       float al_, ah_, bl_, bh_, hvl, hvh, hrl, hrh;
       upk(at[j], al_, ah_);
@@ -175,7 +168,7 @@ __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv
 // Full-circle atan2: during the bisection z sweeps [pi/2, 3pi/2] and h may land anywhere (flow/mobiusflow.py:226-245).
 template <int NP>
 __device__ __forceinline__ void probe_pairs(float zr, float zv, const float* prm, f32x2& Fs) {
-  f32x2 q[NP];
+  f32x2 mn[NP];
   float hr_[2 * NP], hv_[2 * NP];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
@@ -186,16 +179,13 @@ __device__ __forceinline__ void probe_pairs(float zr, float zv, const float* prm
     RNF_MAP2(rc, dd, rcp_approx);
     const f32x2 f = mul2(omw, rc);
     const f32x2 hr = fma2(f, dr, nal), hv = fma2(f, dv, nbe);
-    float mnl, mnh, rl, rh;
     upk(hr, hr_[2 * j], hr_[2 * j + 1]);
     upk(hv, hv_[2 * j], hv_[2 * j + 1]);
-    octant_ratio(hv_[2 * j], hr_[2 * j], mnl, rl);
-    octant_ratio(hv_[2 * j + 1], hr_[2 * j + 1], mnh, rh);
-    q[j] = mul2(pk(mnl, mnh), pk(rl, rh));
+    mn[j] = pk(fminf(fabsf(hv_[2 * j]), fabsf(hr_[2 * j])), fminf(fabsf(hv_[2 * j + 1]), fabsf(hr_[2 * j + 1])));
   }
   f32x2 at[NP];
 #pragma unroll
-  for (int j = 0; j < NP; ++j) at[j] = atan_unit2(q[j]);
+  for (int j = 0; j < NP; ++j) at[j] = asin_unit2(mn[j]);
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     const f32x2 alt = fma2(at[j], bc(-1.0f), bc(1.5707963267948966f));

@@ -80,12 +80,24 @@ def test_softplus_series_branch():
     assert abs(float(m.group(2)) - 1 / np.log(2)) < 1e-12 and abs(float(m.group(1)) + 0.5 / np.log(2)) < 1e-12
 
 
-def test_packed_atan_uses_the_same_polynomial():
-    """mobius_pair.cuh evaluates atan for two components per instruction with the coefficients of atan2_wrapped_fast."""
+def test_packed_asin_polynomial_accuracy():
+    """mobius_pair.cuh takes the angle of the unit vector h from its nearer axis as asin(min(|h.r|, |h.v|)) (no division):
+    float32 Horner emulation of the polynomial read back from the header, against asin on [0, 1/sqrt 2]."""
     src = open(os.path.join(ROOT, "rotationnormflow_b200", "csrc", "mobius_pair.cuh")).read()
-    body = src[src.index("f32x2 atan_unit2"):src.index("octant_ratio")]
-    packed = [float(v) for v in re.findall(r"bc\((-?[0-9.e-]+)f\)", body)]
-    assert packed == _coeffs()[::-1]
+    body = src[src.index("f32x2 asin_unit2"):src.index("// NP pairs of mixture components")]
+    co = [float(v) for v in re.findall(r"bc\((-?[0-9.e-]+)f\)", body)]          # highest power first
+    assert len(co) == 7
+    m = np.linspace(0, 0.70711, 1_000_001).astype(np.float32)
+    s = (m.astype(np.float64) * m).astype(np.float32)
+    p = np.full_like(s, np.float32(co[0]))
+    for c in co[1:]:
+        p = _fma32(p, s, np.float32(c))
+    ps = (p.astype(np.float64) * s).astype(np.float32)
+    res = (ps.astype(np.float64) * m + m).astype(np.float32)
+    assert np.abs(res.astype(np.float64) - np.arcsin(m.astype(np.float64))).max() < 6e-8
+    # unit vector: atan(min / max) == asin(min)
+    t = np.linspace(0, np.pi / 4, 1001)
+    assert np.abs(np.arctan(np.sin(t) / np.cos(t)) - np.arcsin(np.sin(t))).max() < 1e-15
 
 
 def test_sincos_2pi_accuracy():
