@@ -35,6 +35,9 @@ namespace {
 #ifndef RNF_T4_TILES
 #define RNF_T4_TILES 4           // tiles in flight per SM (4 = TMEM and register-file ceiling at 128 registers per thread)
 #endif
+#ifndef RNF_T4_FHFMA
+#define RNF_T4_FHFMA 0
+#endif
 #ifndef RNF_T4_NP
 #define RNF_T4_NP 2              // mixture pairs evaluated together
 #endif
@@ -92,9 +95,11 @@ __device__ __forceinline__ uint32_t pack_h2(__half lo, __half hi) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// ReLU + error-compensated fp16 split of two activations (tc_common.cuh: relu_split2); the residual x - hi is one mixed-
-// precision FMA per element (sm_100 FHFMA: f16 * f16 + f32 -> f32, exact here), no unpacking of hi.
+// ReLU + error-compensated fp16 split of two activations (tc_common.cuh: relu_split2) with the residual taken packed.
+// (The mixed-precision FHFMA form of the residual, fma.rn.f32.f16, issues one instruction less but runs at a quarter of the
+// FMA rate: tools/cvt_rate.cu.)
 __device__ __forceinline__ void relu_split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+#if RNF_T4_FHFMA
   asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
   float d0, d1;
   asm("{\n"
@@ -107,6 +112,13 @@ __device__ __forceinline__ void relu_split_pair(float x0, float x1, uint32_t& hi
       : "=f"(d0), "=f"(d1)
       : "r"(hi), "f"(x0), "f"(x1));
   asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
+#else
+  asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  float d0, d1;
+  upk(sub2(pk(x0, x1), pk(back.x, back.y)), d0, d1);
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
+#endif
 }
 
 // Epilogue of one GEMM: my row of the accumulator -> (+ c) -> ReLU -> fp16 hi / lo -> A operand in TMEM (K element 2e in the
