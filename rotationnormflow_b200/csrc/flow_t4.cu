@@ -405,7 +405,9 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
       }
 #else
         float buf0[16], buf1[16];
+        if (c == 2) TRACE(30);                        // 30 / 31: how long chunk 2's MMAs keep the tile waiting
         wait_mma();
+        if (c == 2) TRACE(31);
         TRACE(14 + c);
         W4_DONE();
         tmem_ld16_async(tm + kColD, buf0);

@@ -36,4 +36,4 @@ for s in range(2, 6):
         base = int(row[0])
         print(f"step {40+s} tile {tile}: start @{base - t0:7d} | " + " ".join(f"{names[i]}+{int(row[i]) - int(row[i-1])}" for i in range(1, last + 1))
               + f" | total {int(row[last]) - base}"
-              + (" | weight waits " + " ".join(str(int(row[21 + 2 * k]) - int(row[20 + 2 * k])) for k in range(5)) if mode == "tc" else ""))
+              + (" | weight waits " + " ".join(str(int(row[21 + 2 * k]) - int(row[20 + 2 * k])) for k in range(5)) + f" | chunk-2 MMA wait {int(row[31]) - int(row[30])}" if mode == "tc" else ""))
