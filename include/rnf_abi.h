@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RNF_ABI_VERSION 5
+#define RNF_ABI_VERSION 6
 
 /* error codes */
 #define RNF_OK 0
@@ -142,6 +142,21 @@ int rnf_grid_logprob(rnf_flow* flow, const float* grid_dev, int64_t G, int64_t g
                      const float* cond_dev, int64_t B, const float* fisher_A_dev, const float* fisher_c_dev,
                      float* logp_out_dev, float* part_dev, float* max_out_dev, int64_t* argmax_out_dev,
                      float* sumexp_out_dev, int mlp_mode, void* stream);
+
+/*
+ * The same with the spread metric of the north star fused into the reduction epilogue (the reference has
+ * no implementation of it -- it is the probability-weighted version of its own min_geodesic_distance_rotmats,
+ * utils/utils.py:231-235):  per image  sum_g exp(logp[b,g] - max_b) * min_k angle(grid[g] @ offset, gt[b,k]).
+ *   gt_dev             [B,gt_k,3,3] ground-truth rotations per image (gt_k >= 1 symmetric equivalents)
+ *   spread_num_out_dev [B] float: the numerator above; spread_b = spread_num / sumexp (radians); partial sums of several
+ *                      grid slices / ranks merge like sumexp (rescale by exp(max_r - max) and add).
+ * gt_dev == NULL and spread_num_out_dev == NULL: identical to rnf_grid_logprob.
+ */
+int rnf_grid_logprob_spread(rnf_flow* flow, const float* grid_dev, int64_t G, int64_t g_index0, const float* offset_dev,
+                            const float* cond_dev, int64_t B, const float* fisher_A_dev, const float* fisher_c_dev,
+                            const float* gt_dev, int gt_k, float* logp_out_dev, float* part_dev, float* max_out_dev,
+                            int64_t* argmax_out_dev, float* sumexp_out_dev, float* spread_num_out_dev, int mlp_mode,
+                            void* stream);
 
 /*
  * generate_healpix_grid (utils/sd.py:48-82): rotations [begin,end) of the level-`level` grid

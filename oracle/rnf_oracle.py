@@ -409,6 +409,16 @@ def min_geodesic_distance_rotmats(r1s: torch.Tensor, r2s: torch.Tensor) -> torch
     return torch.acos(torch.clip((prod.max(-1).values - 1.0) / 2.0, -1.0, 1.0))
 
 
+def spread(logp: torch.Tensor, samples: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """Spread of the north star (IPDF-style; the reference has no implementation): per image
+    sum_g p_g d(R_g, R_gt) / sum_g p_g with p_g = exp(logp[b,g]) and d = min_geodesic_distance_rotmats (utils/utils.py:231-235).
+    logp [B,G], samples [G,3,3] (the evaluation points grid @ offset), gt [B,K,3,3] -> [B] radians (float64)."""
+    w = torch.softmax(logp.double(), dim=-1)
+    prod = torch.einsum("gij,bkij->bgk", samples.double(), gt.double())
+    d = torch.acos(torch.clip((prod.max(-1).values - 1.0) / 2.0, -1.0, 1.0))
+    return (w * d).sum(-1)
+
+
 def random_rotations(n: int, generator: torch.Generator | None = None, dtype=torch.float32) -> torch.Tensor:
     """Haar-uniform rotations from normalised Gaussian quaternions (public pytorch3d definition)."""
     o = torch.randn((n, 4), generator=generator, dtype=torch.float64)

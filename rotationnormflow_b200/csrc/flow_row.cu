@@ -203,6 +203,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
     }
     const float* cond_img = a.cond != nullptr ? a.cond + img * a.cond_stride : nullptr;
     float ldj = 0.0f;
+    float dgt = 0.0f;                                  // spread metric: angle of the evaluation point to the image's ground truth
+    if (GRID && a.gt != nullptr && valid) dgt = gt_distance(a.gt + img * a.gt_k * 9, a.gt_k, R);
 
 #pragma unroll 1
     for (int lstep = 0; lstep < a.n_layers; ++lstep) {
@@ -456,16 +458,21 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
       }
       const float m = bv;
       float e = (valid && m > -INFINITY) ? expf(lp - m) : 0.0f;
+      float ed = e * dgt;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+      for (int o = 16; o > 0; o >>= 1) {
+        e += __shfl_xor_sync(0xffffffffu, e, o);
+        ed += __shfl_xor_sync(0xffffffffu, ed, o);
+      }
       named_bar(3 + tile, 128);
-      if (lane == 0) s_v[w4] = e;
+      if (lane == 0) { s_v[w4] = e; s_v[4 + w4] = ed; }
       named_bar(3 + tile, 128);
       if (rowi == 0) {
         const float s = (s_v[0] + s_v[1]) + (s_v[2] + s_v[3]);
-        float* p = a.part + tile_idx * 4;
+        float* p = a.part + tile_idx * kPartStride;
         p[0] = m;
         p[1] = s;
+        p[4] = (s_v[4] + s_v[5]) + (s_v[6] + s_v[7]);
         p[2] = __int_as_float((int)(bi & 0xffffffffLL));
         p[3] = __int_as_float((int)(bi >> 32));
       }

@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(T, 1) flow_v1_kernel(const FlowArgs a) {
   float* sW = smem;
   float* sAct = smem + kMobFloats;
   __shared__ float s_red_v[T / 32];
+  __shared__ float s_red_d[T / 32];
   __shared__ long long s_red_i[T / 32];
   __shared__ float s_bcast;
   const int tid = threadIdx.x;
@@ -223,6 +224,8 @@ __global__ void __launch_bounds__(T, 1) flow_v1_kernel(const FlowArgs a) {
     }
     const float* cond_img = a.cond != nullptr ? a.cond + img * a.cond_stride : nullptr;
     float ldj = 0.0f;
+    float dgt = 0.0f;                                  // spread metric: angle of the evaluation point to the image's ground truth
+    if (GRID && a.gt != nullptr && valid) dgt = gt_distance(a.gt + img * a.gt_k * 9, a.gt_k, R);
 
 #pragma unroll 1
     for (int step = 0; step < a.n_layers; ++step) {
@@ -295,18 +298,23 @@ __global__ void __launch_bounds__(T, 1) flow_v1_kernel(const FlowArgs a) {
       const float m = s_bcast;
       const long long mi = s_red_i[0];
       float e = (valid && m > -INFINITY) ? expf(lp - m) : 0.0f;
+      float ed = e * dgt;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+      for (int o = 16; o > 0; o >>= 1) {
+        e += __shfl_xor_sync(0xffffffffu, e, o);
+        ed += __shfl_xor_sync(0xffffffffu, ed, o);
+      }
       __syncthreads();
-      if ((tid & 31) == 0) s_red_v[tid >> 5] = e;
+      if ((tid & 31) == 0) { s_red_v[tid >> 5] = e; s_red_d[tid >> 5] = ed; }
       __syncthreads();
       if (tid == 0) {
-        float s = 0.0f;
+        float s = 0.0f, sd = 0.0f;
 #pragma unroll
-        for (int w = 0; w < T / 32; ++w) s += s_red_v[w];
-        float* p = a.part + tile * 4;
+        for (int w = 0; w < T / 32; ++w) { s += s_red_v[w]; sd += s_red_d[w]; }
+        float* p = a.part + tile * kPartStride;
         p[0] = m;
         p[1] = s;
+        p[4] = sd;
         p[2] = __int_as_float((int)(mi & 0xffffffffLL));
         p[3] = __int_as_float((int)(mi >> 32));
       }
@@ -317,9 +325,9 @@ __global__ void __launch_bounds__(T, 1) flow_v1_kernel(const FlowArgs a) {
 // One CTA per image: fold the per-tile partials in tile (= increasing grid index) order.
 __global__ void grid_combine_kernel(const float* __restrict__ part, int64_t tiles_per_image, int64_t g_index0,
                                     float* __restrict__ max_out, int64_t* __restrict__ argmax_out,
-                                    float* __restrict__ sumexp_out) {
+                                    float* __restrict__ sumexp_out, float* __restrict__ spread_num_out) {
   const int64_t b = blockIdx.x;
-  const float* p = part + b * tiles_per_image * 4;
+  const float* p = part + b * tiles_per_image * kPartStride;
   __shared__ float s_v[32];
   __shared__ long long s_i[32];
   __shared__ float s_m;
@@ -327,8 +335,8 @@ __global__ void grid_combine_kernel(const float* __restrict__ part, int64_t tile
   float bv = -INFINITY;
   long long bi = 0x7fffffffffffffffLL;
   for (int64_t t = tid; t < tiles_per_image; t += blockDim.x) {
-    const float v = p[t * 4];
-    const long long i = ((long long)(unsigned)__float_as_int(p[t * 4 + 2])) | ((long long)__float_as_int(p[t * 4 + 3]) << 32);
+    const float v = p[t * kPartStride];
+    const long long i = ((long long)(unsigned)__float_as_int(p[t * kPartStride + 2])) | ((long long)__float_as_int(p[t * kPartStride + 3]) << 32);
     if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
   }
 #pragma unroll
@@ -353,22 +361,31 @@ __global__ void grid_combine_kernel(const float* __restrict__ part, int64_t tile
   }
   __syncthreads();
   const float m = s_m;
-  float s = 0.0f;
+  float s = 0.0f, sd = 0.0f;
   for (int64_t t = tid; t < tiles_per_image; t += blockDim.x) {
-    const float v = p[t * 4];
-    if (v > -INFINITY) s += p[t * 4 + 1] * expf(v - m);
+    const float v = p[t * kPartStride];
+    if (v > -INFINITY) {
+      const float w = expf(v - m);
+      s += p[t * kPartStride + 1] * w;
+      sd += p[t * kPartStride + 4] * w;
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    sd += __shfl_xor_sync(0xffffffffu, sd, o);
+  }
   __syncthreads();
-  if ((tid & 31) == 0) s_v[tid >> 5] = s;
+  __shared__ float s_d[32];
+  if ((tid & 31) == 0) { s_v[tid >> 5] = s; s_d[tid >> 5] = sd; }
   __syncthreads();
   if (tid == 0) {
-    float tot = 0.0f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_v[w];
+    float tot = 0.0f, totd = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { tot += s_v[w]; totd += s_d[w]; }
     max_out[b] = m;
     argmax_out[b] = (int64_t)s_i[0] + g_index0;
     sumexp_out[b] = tot;
+    if (spread_num_out != nullptr) spread_num_out[b] = totd;       // sum_g exp(logp_g - max) d(R_g, R_gt)
   }
 }
 
@@ -389,9 +406,9 @@ cudaError_t launch_flow_v1(const FlowArgs& a, bool inverse, int sm_count, cudaSt
 }
 
 cudaError_t launch_grid_combine(const float* part, int64_t tiles_per_image, int64_t B, int64_t g_index0, float* max_out,
-                                int64_t* argmax_out, float* sumexp_out, cudaStream_t st) {
+                                int64_t* argmax_out, float* sumexp_out, float* spread_num_out, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  grid_combine_kernel<<<(unsigned)B, 256, 0, st>>>(part, tiles_per_image, g_index0, max_out, argmax_out, sumexp_out);
+  grid_combine_kernel<<<(unsigned)B, 256, 0, st>>>(part, tiles_per_image, g_index0, max_out, argmax_out, sumexp_out, spread_num_out);
   return cudaGetLastError();
 }
 

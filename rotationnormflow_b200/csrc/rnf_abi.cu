@@ -192,13 +192,22 @@ int rnf_flow_inverse(rnf_flow* f, const float* R_in, int64_t N, const float* con
 int64_t rnf_grid_partial_floats(int64_t G, int64_t B) {
   if (G <= 0 || B <= 0) return 0;
   const int64_t tpi = (G + 127) / 128;  // sized for the smaller (tensor-core) tile so either kernel fits
-  return tpi * B * 4;
+  return tpi * B * rnf::kPartStride;
 }
 
 int rnf_grid_logprob(rnf_flow* f, const float* grid_dev, int64_t G, int64_t g_index0, const float* offset_dev,
                      const float* cond_dev, int64_t B, const float* fisher_A_dev, const float* fisher_c_dev,
                      float* logp_out_dev, float* part_dev, float* max_out_dev, int64_t* argmax_out_dev,
                      float* sumexp_out_dev, int mlp_mode, void* stream) {
+  return rnf_grid_logprob_spread(f, grid_dev, G, g_index0, offset_dev, cond_dev, B, fisher_A_dev, fisher_c_dev, nullptr, 0,
+                                 logp_out_dev, part_dev, max_out_dev, argmax_out_dev, sumexp_out_dev, nullptr, mlp_mode, stream);
+}
+
+int rnf_grid_logprob_spread(rnf_flow* f, const float* grid_dev, int64_t G, int64_t g_index0, const float* offset_dev,
+                            const float* cond_dev, int64_t B, const float* fisher_A_dev, const float* fisher_c_dev,
+                            const float* gt_dev, int gt_k, float* logp_out_dev, float* part_dev, float* max_out_dev,
+                            int64_t* argmax_out_dev, float* sumexp_out_dev, float* spread_num_out_dev, int mlp_mode,
+                            void* stream) {
   if (!f) return fail(RNF_EINVAL, "rnf_grid_logprob: null handle");
   if (G < 0 || B < 0) return fail(RNF_EINVAL, "rnf_grid_logprob: negative size");
   if (!valid_mode(mlp_mode)) return fail(RNF_EINVAL, "rnf_grid_logprob: bad mlp_mode %d", mlp_mode);
@@ -208,6 +217,8 @@ int rnf_grid_logprob(rnf_flow* f, const float* grid_dev, int64_t G, int64_t g_in
   if ((fisher_A_dev == nullptr) != (fisher_c_dev == nullptr))
     return fail(RNF_EINVAL, "rnf_grid_logprob: fisher_A and fisher_c must be given together");
   if (f->cond_floats > 0 && !cond_dev) return fail(RNF_ESTATE, "rnf_grid_logprob: conditional flow needs rnf_flow_condition output");
+  if ((gt_dev == nullptr) != (spread_num_out_dev == nullptr) || (gt_dev != nullptr && gt_k <= 0))
+    return fail(RNF_EINVAL, "rnf_grid_logprob_spread: gt [B,K,3,3] (K >= 1) and spread_num_out go together");
   rnf::FlowArgs a;
   memset(&a, 0, sizeof(a));
   a.weights = f->weights_dev;
@@ -226,6 +237,8 @@ int rnf_grid_logprob(rnf_flow* f, const float* grid_dev, int64_t G, int64_t g_in
   a.fisher_c = fisher_c_dev;
   a.logp_out = logp_out_dev;
   a.part = part_dev;
+  a.gt = gt_dev;
+  a.gt_k = gt_k;
   a.trace = g_trace;
   cudaError_t e;
   if (mlp_mode != RNF_MLP_FP32) {
@@ -241,7 +254,7 @@ int rnf_grid_logprob(rnf_flow* f, const float* grid_dev, int64_t G, int64_t g_in
   }
   if (e != cudaSuccess) return cuda_fail(e, "rnf_grid_logprob");
   e = rnf::launch_grid_combine(part_dev, a.tiles_per_image, B, g_index0, max_out_dev, argmax_out_dev, sumexp_out_dev,
-                               (cudaStream_t)stream);
+                               spread_num_out_dev, (cudaStream_t)stream);
   return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_grid_logprob (combine)");
 }
 

@@ -39,6 +39,8 @@ struct LayerDev {
   int64_t w_off_tc;
 };
 
+constexpr int kPartStride = 8;
+
 struct FlowArgs {
   const float* weights;
   const LayerDev* layers;
@@ -63,7 +65,9 @@ struct FlowArgs {
   const float* fisher_A;
   const float* fisher_c;
   float* logp_out;
-  float* part;
+  float* part;        // [n_tiles][kPartStride]: (max, sum exp(lp - max), argmax lo, argmax hi, sum exp(lp - max) * d_gt, -, -, -)
+  const float* gt;    // [B][gt_k][9] ground-truth rotations per image (spread metric), nullptr = not requested
+  int gt_k;
   long long* trace;   // debug builds (-DRNF_TC_TRACE): per-phase clock64() stamps of CTA 0, else unused
 };
 
@@ -83,7 +87,7 @@ struct rnf_flow {
 namespace rnf {
 cudaError_t launch_flow_v1(const FlowArgs& a, bool inverse, int sm_count, cudaStream_t st);
 cudaError_t launch_grid_combine(const float* part, int64_t tiles_per_image, int64_t B, int64_t g_index0, float* max_out,
-                                int64_t* argmax_out, float* sumexp_out, cudaStream_t st);
+                                int64_t* argmax_out, float* sumexp_out, float* spread_num_out, cudaStream_t st);
 cudaError_t launch_condition(const rnf_flow* f, const float* feat, int64_t B, float* cond, cudaStream_t st);
 cudaError_t launch_healpix(int level, int64_t begin, int64_t end, float* out, cudaStream_t st);
 cudaError_t launch_min_geodesic(const float* est, const float* gt, int64_t B, int64_t K, float* out, cudaStream_t st);

@@ -142,6 +142,19 @@ __device__ __forceinline__ float quat_affine_fast(const float* __restrict__ W, f
   return 0.34657359027997264f * l2;                  // 0.5 ln 2
 }
 
+// Geodesic angle from R to the closest of K ground-truth rotations: acos(clip((max_k sum_ij R_ij GT_kij - 1) / 2, -1, 1))
+// (min_geodesic_distance_rotmats, utils/utils.py:231-235).  Weight of the spread metric  sum_g p_g d(R_g, R_gt) / sum_g p_g.
+__device__ __forceinline__ float gt_distance(const float* __restrict__ gt, int K, const float R[9]) {
+  float best = -INFINITY;
+  for (int k = 0; k < K; ++k) {
+    float tr = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) tr = fmaf(R[i], __ldg(gt + k * 9 + i), tr);
+    best = fmaxf(best, tr);
+  }
+  return acosf(fminf(fmaxf((best - 1.0f) * 0.5f, -1.0f), 1.0f));
+}
+
 __host__ __device__ inline float det3f(float a00, float a01, float a02, float a10, float a11, float a12, float a20,
                                        float a21, float a22) {
   const float d00 = a11 * a22 - a12 * a21;

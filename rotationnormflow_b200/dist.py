@@ -23,29 +23,34 @@ def shard_range(G: int, rank: int, world: int) -> tuple[int, int]:
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def merge_partials(mx: torch.Tensor, am: torch.Tensor, se: torch.Tensor):
+def merge_partials(mx: torch.Tensor, am: torch.Tensor, se: torch.Tensor, sn: torch.Tensor | None = None):
     """Merge per-shard partials stacked on dim 0: mx/am/se are [W,B] -> (max [B], argmax [B], sumexp [B]).
 
     Ties on the maximum resolve to the smallest global index (torch.argmax / first-index semantics of
-    agent.py:264, eval.py:461).  Shards holding no rotations carry max = -inf and sumexp = 0."""
+    agent.py:264, eval.py:461).  Shards holding no rotations carry max = -inf and sumexp = 0.
+    ``sn`` [W,B] (spread numerators, relative to each shard's max) is rescaled and summed like sumexp and returned fourth."""
     m = mx.max(dim=0).values
     cand = torch.where(mx == m[None, :], am, torch.full_like(am, torch.iinfo(torch.int64).max))
     idx = cand.min(dim=0).values
     scale = torch.where(torch.isfinite(mx), torch.exp(mx.double() - m.double()[None, :]), torch.zeros_like(mx, dtype=torch.float64))
     s = (se.double() * scale).sum(dim=0)
+    if sn is not None:
+        return m, idx, s.to(se.dtype), (sn.double() * scale).sum(dim=0).to(sn.dtype)
     return m, idx, s.to(se.dtype)
 
 
-def all_merge(mx: torch.Tensor, am: torch.Tensor, se: torch.Tensor, group=None):
-    """One all-gather of the packed partials, then ``merge_partials`` on every rank."""
+def all_merge(mx: torch.Tensor, am: torch.Tensor, se: torch.Tensor, group=None, sn: torch.Tensor | None = None):
+    """One all-gather of the packed partials ([B,3] float64, [B,4] with spread numerators), then ``merge_partials`` on every rank."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return mx, am, se
+        return (mx, am, se) if sn is None else (mx, am, se, sn)
     world = dist.get_world_size(group)
-    packed = torch.stack([mx.double(), am.double(), se.double()], dim=1).contiguous()      # [B,3]; indices < 2^53 are exact
-    flat = torch.empty((world * packed.shape[0], 3), dtype=packed.dtype, device=packed.device)
+    cols = [mx.double(), am.double(), se.double()] + ([] if sn is None else [sn.double()])   # indices < 2^53 are exact
+    packed = torch.stack(cols, dim=1).contiguous()
+    flat = torch.empty((world * packed.shape[0], len(cols)), dtype=packed.dtype, device=packed.device)
     dist.all_gather_into_tensor(flat, packed, group=group)                                  # rank-major concatenation
-    gathered = flat.view(world, packed.shape[0], 3)
-    return merge_partials(gathered[:, :, 0].to(mx.dtype), gathered[:, :, 1].to(torch.int64), gathered[:, :, 2].to(se.dtype))
+    gathered = flat.view(world, packed.shape[0], len(cols))
+    return merge_partials(gathered[:, :, 0].to(mx.dtype), gathered[:, :, 1].to(torch.int64), gathered[:, :, 2].to(se.dtype),
+                          None if sn is None else gathered[:, :, 3].to(sn.dtype))
 
 
 def log_normaliser(mx: torch.Tensor, se: torch.Tensor, G_total: int) -> torch.Tensor:
@@ -54,8 +59,12 @@ def log_normaliser(mx: torch.Tensor, se: torch.Tensor, G_total: int) -> torch.Te
 
 
 def sharded_grid_log_prob(flow, grid_shard: torch.Tensor, g_index0: int, G_total: int, feature=None, offset=None,
-                          fisher_A=None, group=None, mlp_mode=None):
-    """Per-image (max, argmax, log-normaliser) over a grid whose slices live on different ranks."""
-    out = flow.grid_log_prob(grid_shard, feature, offset=offset, fisher_A=fisher_A, g_index0=g_index0, mlp_mode=mlp_mode)
+                          fisher_A=None, group=None, mlp_mode=None, gt_rotations=None):
+    """Per-image (max, argmax, log-normaliser[, spread]) over a grid whose slices live on different ranks."""
+    out = flow.grid_log_prob(grid_shard, feature, offset=offset, fisher_A=fisher_A, g_index0=g_index0, mlp_mode=mlp_mode,
+                             gt_rotations=gt_rotations)
+    if gt_rotations is not None:
+        mx, am, se, sn = all_merge(out["max"], out["argmax"], out["sumexp"], group, sn=out["spread_num"])
+        return dict(max=mx, argmax=am, sumexp=se, log_norm=log_normaliser(mx, se, G_total), spread=sn / se)
     mx, am, se = all_merge(out["max"], out["argmax"], out["sumexp"], group)
     return dict(max=mx, argmax=am, sumexp=se, log_norm=log_normaliser(mx, se, G_total))

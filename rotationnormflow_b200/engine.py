@@ -357,7 +357,8 @@ class Program:
         return R_out, ldj
 
     def grid_logprob(self, grid: torch.Tensor, g_index0: int, offset, cond, B: int, fisher_A, fisher_c,
-                     want_logp: bool, mode: str):
+                     want_logp: bool, mode: str, gt: torch.Tensor | None = None):
+        """-> (max [B], argmax [B], sumexp [B], logp [B,G] | None[, spread_num [B] when gt [B,K,3,3] is given])."""
         G = grid.shape[0]
         dev = self.device
         mx = torch.empty((B,), device=dev, dtype=torch.float32)
@@ -366,6 +367,15 @@ class Program:
         logp = torch.empty((B, G), device=dev, dtype=torch.float32) if want_logp else None
         part = torch.empty((max(1, int(self.lib.rnf_grid_partial_floats(G, B))),), device=dev, dtype=torch.float32)
         vp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        if gt is not None:
+            gt = gt.to(dev, torch.float32).reshape(B, -1, 9).contiguous()
+            sn = torch.empty((B,), device=dev, dtype=torch.float32)
+            with torch.cuda.device(dev):
+                _cabi.check(self.lib.rnf_grid_logprob_spread(self.handle, vp(grid), G, int(g_index0), vp(offset), vp(cond), B,
+                                                             vp(fisher_A), vp(fisher_c), vp(gt), int(gt.shape[1]), vp(logp),
+                                                             vp(part), vp(mx), vp(am), vp(se), vp(sn), _MODES[mode],
+                                                             self._stream()))
+            return mx, am, se, logp, sn
         with torch.cuda.device(dev):
             _cabi.check(self.lib.rnf_grid_logprob(self.handle, vp(grid), G, int(g_index0), vp(offset), vp(cond), B,
                                                   vp(fisher_A), vp(fisher_c), vp(logp), vp(part), vp(mx), vp(am), vp(se),

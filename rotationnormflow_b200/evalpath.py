@@ -24,13 +24,15 @@ def _random_rotation(device, generator=None):
 
 
 @torch.no_grad()
-def estimate_rotation_grid(flow, feature, number_queries, fisher_A=None, offset=None, generator=None, mlp_mode=None):
-    """Returns (est_rotation [B,3,3], dict(max, argmax, sumexp)).  One random right-offset per batch (eval.py:439-440)."""
+def estimate_rotation_grid(flow, feature, number_queries, fisher_A=None, offset=None, generator=None, mlp_mode=None,
+                           gt_rotations=None):
+    """Returns (est_rotation [B,3,3], dict(max, argmax, sumexp[, spread])).  One random right-offset per batch
+    (eval.py:439-440).  gt_rotations [B,K,3,3] adds the probability-weighted angular error (spread) of the same pass."""
     dev = feature.device
     grid = rgrid.get_closest_available_grid(number_queries, dev)
     if offset is None:
         offset = _random_rotation(dev, generator)
-    out = flow.grid_log_prob(grid, feature, offset=offset, fisher_A=fisher_A, mlp_mode=mlp_mode)
+    out = flow.grid_log_prob(grid, feature, offset=offset, fisher_A=fisher_A, mlp_mode=mlp_mode, gt_rotations=gt_rotations)
     est = grid[out["argmax"]] @ offset.to(dev)
     return est, out
 

@@ -373,12 +373,16 @@ class Flow(nn.Module):
         return self.forward(rotation, feature, True, draw, feature_index, mlp_mode)
 
     # ---- N1: the loops of eval.py:444-462 / agent.py:246-266 as one call -------------------
-    def grid_log_prob(self, grid, feature=None, offset=None, fisher_A=None, return_logp=False, g_index0=0, mlp_mode=None):
+    def grid_log_prob(self, grid, feature=None, offset=None, fisher_A=None, return_logp=False, g_index0=0, mlp_mode=None,
+                      gt_rotations=None):
         """log p(grid[g] @ offset | image b) for all b, g, reduced per image on the fly.
 
         grid [G,3,3] (this rank's slice; ``g_index0`` = global index of grid[0]); feature [B,F] one row per image
         (None for an unconditional flow -> B = 1); fisher_A [B,3,3] adds the matrix-Fisher base term
         (utils/fisher.py:217-232, image-major as at agent.py:246-251).
+        gt_rotations [B,K,3,3] (K >= 1 equivalent ground truths per image) adds the spread metric
+        sum_g p_g d(grid[g] @ offset, R_gt) / sum_g p_g, d = angle to the closest ground truth (utils/utils.py:231-235),
+        fused into the same pass: ``spread`` [B] in radians over THIS slice and ``spread_num`` [B] for merging slices.
         Returns dict(max [B], argmax [B] int64 global grid index (first on ties), sumexp [B] = sum_g exp(logp - max),
         logp [B,G] if requested)."""
         from .fisher import fisher_constants
@@ -396,8 +400,15 @@ class Flow(nn.Module):
             if A9.shape[0] != B:
                 raise ValueError("fisher_A must have one 3x3 matrix per image")
         off = None if offset is None else offset.to(G_.device, torch.float32).contiguous()
-        mx, am, se, logp = prog.grid_logprob(G_, g_index0, off, cond, B, A9, c, return_logp, mlp_mode or engine.default_mlp_mode())
-        out = dict(max=mx, argmax=am, sumexp=se)
+        mode = mlp_mode or engine.default_mlp_mode()
+        if gt_rotations is not None:
+            if gt_rotations.shape[0] != B or tuple(gt_rotations.shape[-2:]) != (3, 3):
+                raise ValueError("gt_rotations must be [B,K,3,3] with one set of ground truths per image")
+            mx, am, se, logp, sn = prog.grid_logprob(G_, g_index0, off, cond, B, A9, c, return_logp, mode, gt=gt_rotations)
+            out = dict(max=mx, argmax=am, sumexp=se, spread_num=sn, spread=sn / se)
+        else:
+            mx, am, se, logp = prog.grid_logprob(G_, g_index0, off, cond, B, A9, c, return_logp, mode)
+            out = dict(max=mx, argmax=am, sumexp=se)
         if return_logp:
             out["logp"] = logp
         return out

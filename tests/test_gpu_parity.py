@@ -310,6 +310,38 @@ def test_eval_call_sites():
         assert (est[b] - samples[b, k]).abs().max() == 0
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_spread_metric_fused_in_the_grid_pass(mode):
+    """sum_g p_g d(R_g, R_gt) / sum_g p_g from the reduction epilogue == the oracle's definition on the oracle's log-probs;
+    two grid slices merge to the same value; K = 1 and K = 3 ground truths per image."""
+    from rotationnormflow_b200 import dist as rdist
+    g = golden("s_symsol")
+    m = _product(g)
+    B = 3
+    feat = g.feat[:B].cuda()
+    grid = orc.healpix_grid(1).float()                                   # 576 rotations
+    gen = torch.Generator().manual_seed(11)
+    off = orc.random_rotations(1, gen)[0]
+    samples = grid @ off
+    o = orc.OracleFlow(g.cfg, g.state_dict(), torch.float64)
+    G = grid.shape[0]
+    _, ldj = o.forward(samples.double().repeat(B, 1, 1), g.feat[:B].double().repeat_interleave(G, 0))
+    logp = ldj.reshape(B, G)
+    for K in (1, 3):
+        gt = orc.random_rotations(B * K, gen).reshape(B, K, 3, 3)
+        want = orc.spread(logp, samples, gt)
+        with torch.no_grad():
+            out = m.grid_log_prob(grid.cuda(), feat, offset=off.cuda(), gt_rotations=gt.cuda(), mlp_mode=mode)
+            assert (out["spread"].cpu().double() - want).abs().max() < 2e-4 * max(1.0, float(want.max()))
+            assert torch.equal(out["argmax"].cpu(), torch.argmax(logp, dim=-1))
+            a = m.grid_log_prob(grid[:200].cuda(), feat, offset=off.cuda(), gt_rotations=gt.cuda(), mlp_mode=mode)
+            b = m.grid_log_prob(grid[200:].cuda(), feat, offset=off.cuda(), gt_rotations=gt.cuda(), g_index0=200, mlp_mode=mode)
+        mx, am, se, sn = rdist.merge_partials(torch.stack([a["max"], b["max"]]), torch.stack([a["argmax"], b["argmax"]]),
+                                              torch.stack([a["sumexp"], b["sumexp"]]), torch.stack([a["spread_num"], b["spread_num"]]))
+        assert torch.equal(am, out["argmax"])
+        assert ((sn / se) - out["spread"]).abs().max() < 1e-5
+
+
 def test_geodesic_metrics():
     from rotationnormflow_b200 import metrics
     gen = torch.Generator().manual_seed(9)

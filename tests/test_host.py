@@ -195,7 +195,7 @@ def test_cabi_argument_errors_without_gpu():
     assert lib.rnf_healpix_grid(9, 0, 1, None, None) == -1
     assert b"level" in lib.rnf_last_error()
     assert lib.rnf_flow_forward(None, None, 1, None, 0, None, 0, None, None, 0, None) == -1
-    assert lib.rnf_grid_partial_floats(1000, 2) == ((1000 + 127) // 128) * 2 * 4
+    assert lib.rnf_grid_partial_floats(1000, 2) == ((1000 + 127) // 128) * 2 * 8    # kPartStride floats per tile
     with pytest.raises(_cabi.RnfError):
         _cabi.check(lib.rnf_flow_condition(None, None, 1, None, None))
 
@@ -233,6 +233,31 @@ def test_shard_ranges_cover_the_grid():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
             sizes = [e - b for b, e in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_merge_partials_with_spread_numerators():
+    """Slices merged with their spread numerators give the spread of the whole grid (oracle definition)."""
+    rng = torch.Generator().manual_seed(5)
+    B, G = 3, 1000
+    logp = torch.randn(B, G, generator=rng) * 3
+    samples = orc.random_rotations(G, rng)
+    gt = orc.random_rotations(B * 2, rng).reshape(B, 2, 3, 3)
+    want = orc.spread(logp, samples, gt)
+    prod = torch.einsum("gij,bkij->bgk", samples.double(), gt.double())
+    d = torch.acos(torch.clip((prod.max(-1).values - 1.0) / 2.0, -1.0, 1.0))
+    cuts = [0, 100, 100, 640, G]                                         # includes an empty slice
+    mx, am, se, sn = [], [], [], []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        if hi == lo:
+            mx.append(torch.full((B,), -float("inf"))); am.append(torch.zeros(B, dtype=torch.int64))
+            se.append(torch.zeros(B)); sn.append(torch.zeros(B))
+            continue
+        m = logp[:, lo:hi].max(dim=-1)
+        e = torch.exp(logp[:, lo:hi].double() - m.values[:, None].double())
+        mx.append(m.values); am.append(m.indices + lo); se.append(e.sum(-1).float()); sn.append((e * d[:, lo:hi]).sum(-1).float())
+    m, idx, s, n = rdist.merge_partials(torch.stack(mx), torch.stack(am), torch.stack(se), torch.stack(sn))
+    assert torch.equal(idx, torch.argmax(logp, dim=-1))
+    assert ((n.double() / s.double()) - want).abs().max() < 1e-6
 
 
 def test_merge_partials_equals_global_reduction():
