@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RNF_ABI_VERSION 6
+#define RNF_ABI_VERSION 7
 
 /* error codes */
 #define RNF_OK 0
@@ -163,6 +163,17 @@ int rnf_grid_logprob_spread(rnf_flow* flow, const float* grid_dev, int64_t G, in
  * (72*8^level rotations, index = tilt*npix + pixel, RING pixel order), float64 math -> float32.
  */
 int rnf_healpix_grid(int level, int64_t begin, int64_t end, float* R_out_dev, void* stream);
+
+/*
+ * MatrixFisherN._sample / sample_matrix_fisher (utils/fisher.py:117-207,234-243): n_per_image rotations per image from the
+ * matrix-Fisher distribution with parameter A_b = U_b diag(S_b) V_b^T (proper SVD, utils/fisher.py:48-64), by rejection from
+ * the angular-central-Gaussian envelope of the equivalent Bingham distribution on quaternions (b = 1.5).
+ *   usv_dev   [B,24]: U (9, row-major), proper S (3), V (9), 3 pad floats
+ *   seed      selects the random stream (Philox4x32-10 keyed by seed, counter = sample index / attempt): reproducible
+ *             per (seed, B, n_per_image), independent of torch's generator -- parity with the reference is distributional
+ *   R_out_dev [B,n_per_image,3,3]
+ */
+int rnf_fisher_sample(const float* usv_dev, int64_t B, int64_t n_per_image, uint64_t seed, float* R_out_dev, void* stream);
 
 /*
  * MatrixFisherN._log_prob (utils/fisher.py:217-232) for image-major rows: R_dev [N,3,3] with N = B * rows_per_image,

@@ -409,6 +409,33 @@ def min_geodesic_distance_rotmats(r1s: torch.Tensor, r2s: torch.Tensor) -> torch
     return torch.acos(torch.clip((prod.max(-1).values - 1.0) / 2.0, -1.0, 1.0))
 
 
+def sample_matrix_fisher(A: torch.Tensor, num_samples: int, generator: torch.Generator | None = None, b: float = 1.5,
+                         oversampling_ratio: int = 8) -> torch.Tensor:
+    """utils/fisher.py:117-207 (sample_bingham + sample_matrix_fisher) for ONE image, float64: batched rejection from the
+    ACG envelope, first ``num_samples`` accepted candidates, R = U quat_to_rotmat(q) V^T with the proper SVD (:48-64)."""
+    A = A.double()
+    U, S, Vh = torch.linalg.svd(A)
+    V = Vh.T.clone(); U = U.clone(); S = S.clone()
+    dU, dV = torch.linalg.det(U), torch.linalg.det(V)
+    U[:, 2] *= dU; V[:, 2] *= dV; S[2] *= dU * dV
+    lam = torch.stack([torch.zeros((), dtype=torch.float64), 2 * (S[1] + S[2]), 2 * (S[0] + S[2]), 2 * (S[0] + S[1])])
+    omega = 1.0 + 2.0 * lam / b
+    std = omega ** -0.5
+    m_star = math.exp(-(4 - b) / 2) * (4 / b) ** 2
+    while True:
+        eps = torch.randn(num_samples * oversampling_ratio, 4, generator=generator, dtype=torch.float64)
+        y = std * eps
+        q = y / y.norm(dim=1, keepdim=True)
+        p_bing = torch.exp(-(q * lam * q).sum(-1))
+        p_acg = (q * omega * q).sum(-1) ** -2
+        w = torch.rand(num_samples * oversampling_ratio, generator=generator, dtype=torch.float64)
+        acc = w < p_bing / (m_star * p_acg)
+        if int(acc.sum()) >= num_samples:
+            q = q[acc][:num_samples]
+            break
+    return U @ quaternion_to_matrix(q) @ V.T
+
+
 def spread(logp: torch.Tensor, samples: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
     """Spread of the north star (IPDF-style; the reference has no implementation): per image
     sum_g p_g d(R_g, R_gt) / sum_g p_g with p_g = exp(logp[b,g]) and d = min_geodesic_distance_rotmats (utils/utils.py:231-235).

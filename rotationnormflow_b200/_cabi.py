@@ -11,7 +11,7 @@ import threading
 
 from . import build as _build
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 RNF_LAYER_MOBIUS = 0
 RNF_LAYER_AFFINE = 1
@@ -69,6 +69,7 @@ _SIGNATURES = {
     "rnf_flow_inverse": (C.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P, C.c_int, _P]),
     "rnf_grid_partial_floats": (_I64, [_I64, _I64]),
     "rnf_grid_logprob": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
+    "rnf_fisher_sample": (C.c_int, [_P, _I64, _I64, C.c_uint64, _P, _P]),
     "rnf_grid_logprob_spread": (C.c_int, [_P, _P, _I64, _I64, _P, _P, _I64, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, _P]),
     "rnf_healpix_grid": (C.c_int, [C.c_int, _I64, _I64, _P, _P]),
     "rnf_fisher_log_prob": (C.c_int, [_P, _P, _I64, _P, _I64, _P, _P]),

@@ -269,6 +269,14 @@ int rnf_healpix_grid(int level, int64_t begin, int64_t end, float* R_out_dev, vo
   return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_healpix_grid");
 }
 
+int rnf_fisher_sample(const float* usv_dev, int64_t B, int64_t n_per_image, uint64_t seed, float* R_out_dev, void* stream) {
+  if (B < 0 || n_per_image < 0) return fail(RNF_EINVAL, "rnf_fisher_sample: negative size");
+  if (B == 0 || n_per_image == 0) return RNF_OK;
+  if (!usv_dev || !R_out_dev) return fail(RNF_EINVAL, "rnf_fisher_sample: null buffer");
+  cudaError_t e = rnf::launch_fisher_sample(usv_dev, B, n_per_image, (unsigned long long)seed, R_out_dev, (cudaStream_t)stream);
+  return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_fisher_sample");
+}
+
 int rnf_fisher_log_prob(const float* A9_dev, const float* c_dev, int64_t B, const float* R_dev, int64_t N, float* out_dev,
                         void* stream) {
   if (B <= 0 || N < 0) return fail(RNF_EINVAL, "rnf_fisher_log_prob: bad sizes");

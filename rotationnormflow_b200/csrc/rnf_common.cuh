@@ -86,6 +86,7 @@ struct rnf_flow {
 // kernel launchers (defined in the .cu files)
 namespace rnf {
 cudaError_t launch_flow_v1(const FlowArgs& a, bool inverse, int sm_count, cudaStream_t st);
+cudaError_t launch_fisher_sample(const float* usv, int64_t B, int64_t n, unsigned long long seed, float* out, cudaStream_t st);
 cudaError_t launch_grid_combine(const float* part, int64_t tiles_per_image, int64_t B, int64_t g_index0, float* max_out,
                                 int64_t* argmax_out, float* sumexp_out, float* spread_num_out, cudaStream_t st);
 cudaError_t launch_condition(const rnf_flow* f, const float* feat, int64_t B, float* cond, cudaStream_t st);

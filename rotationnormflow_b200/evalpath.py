@@ -38,12 +38,29 @@ def estimate_rotation_grid(flow, feature, number_queries, fisher_A=None, offset=
 
 
 @torch.no_grad()
-def estimate_rotation_sampling(flow, feature, number_queries, base_samples=None, base_ll=None, mlp_mode=None):
-    """agent.py:238-266 with a uniform base distribution: the same `number_queries` base rotations for every image
-    (sd.generate_queries + repeat, agent.py:253-256), pushed through Flow.inverse; arg-max of -ldj (+ base_ll) per image.
+def estimate_rotation_sampling(flow, feature, number_queries, base_samples=None, base_ll=None, mlp_mode=None,
+                               fisher_A=None, seed=None):
+    """agent.py:238-266: base rotations pushed through Flow.inverse; arg-max of -ldj + base_ll per image.
+
+    Uniform base (default): the same `number_queries` rotations for every image (sd.generate_queries + repeat,
+    agent.py:253-256).  ``fisher_A`` [B,3,3] (config.pretrain_fisher, agent.py:247-251): per-image samples from
+    MatrixFisherN(A) drawn on the device, with their base log-likelihood.
     Returns (est_rotation [B,3,3], samples [B,Q,3,3], log_prob [B,Q])."""
     dev = feature.device
     B = feature.shape[0]
+    if fisher_A is not None:
+        from .fisher import MatrixFisherN
+        pre = MatrixFisherN(fisher_A.to(dev))
+        base = pre._sample(number_queries, seed=seed)                  # [B,Q,3,3]
+        Q = base.shape[1]
+        rows = base.reshape(-1, 3, 3)
+        base_ll = pre._log_prob(rows).reshape(B, Q)
+        idx = torch.arange(B, device=dev, dtype=torch.int32).repeat_interleave(Q)
+        samples, ldj = flow.inverse(rows, feature, feature_index=idx, mlp_mode=mlp_mode)
+        log_prob = -ldj.reshape(B, Q) + base_ll
+        best = torch.argmax(log_prob, dim=-1)
+        samples = samples.reshape(B, Q, 3, 3)
+        return samples[torch.arange(B, device=dev), best], samples, log_prob
     if base_samples is None:
         base_samples = rgrid.generate_queries(number_queries, "random", dev)
     Q = base_samples.shape[0]

@@ -308,6 +308,26 @@ def test_eval_call_sites():
         k = int(logp[b].argmax())
         assert float(ref.max() - ref[k]) < 5e-3
         assert (est[b] - samples[b, k]).abs().max() == 0
+    # sampling with the matrix-Fisher base (agent.py:247-251): base samples drawn on the device, then the same path;
+    # the returned log-probs are the oracle's inverse-flow log-dets of those very samples plus the base log-likelihood
+    gm = golden("s_modelnet")
+    mm = _product(gm)
+    om = orc.OracleFlow(gm.cfg, gm.state_dict(), torch.float64)
+    fm = gm.feat.cuda()
+    Bm = fm.shape[0]
+    A = torch.randn(Bm, 3, 3, generator=torch.Generator().manual_seed(8)) * 2.0
+    est, samples, logp = evalpath.estimate_rotation_sampling(mm, fm, 200, fisher_A=A.cuda(), seed=77)
+    assert samples.shape == (Bm, 200, 3, 3) and logp.shape == (Bm, 200)
+    from rotationnormflow_b200.fisher import MatrixFisherN
+    pre = MatrixFisherN(A.cuda())
+    base = pre._sample(200, seed=77)
+    for b in range(Bm):
+        Ri, li = om.inverse(base[b].cpu().double(), gm.feat[b:b + 1].double().expand(200, -1))
+        ref = -li + orc.fisher_log_prob(A[b:b + 1].double(), base[b].cpu().double())
+        close = (logp[b].cpu().double() - ref).abs() < 5e-3 * ref.abs().clamp(min=1.0)
+        assert close.float().mean() > 0.95
+        k = int(logp[b].argmax())
+        assert (est[b] - samples[b, k]).abs().max() == 0
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -340,6 +360,31 @@ def test_spread_metric_fused_in_the_grid_pass(mode):
                                               torch.stack([a["sumexp"], b["sumexp"]]), torch.stack([a["spread_num"], b["spread_num"]]))
         assert torch.equal(am, out["argmax"])
         assert ((sn / se) - out["spread"]).abs().max() < 1e-5
+
+
+def test_matrix_fisher_sampling_on_device():
+    """MatrixFisherN._sample (csrc/fisher_sample.cu) against the oracle sampler (utils/fisher.py:117-207 restated): valid
+    rotations, reproducible per seed, first and second moments equal within Monte-Carlo error, per image."""
+    from rotationnormflow_b200.fisher import MatrixFisherN
+    gen = torch.Generator().manual_seed(17)
+    B, n = 3, 200000
+    U, V = orc.random_rotations(B, gen, torch.float64), orc.random_rotations(B, gen, torch.float64)
+    S = torch.tensor([[3.0, 2.0, -1.0], [12.0, 7.0, 5.0], [0.6, 0.3, 0.1]], dtype=torch.float64)
+    A = U @ torch.diag_embed(S) @ V.transpose(1, 2)
+    d = MatrixFisherN(A.float().cuda())
+    R = d._sample(n, seed=1234)
+    assert R.shape == (B, n, 3, 3)
+    assert torch.equal(R, d._sample(n, seed=1234)) and not torch.equal(R, d._sample(n, seed=1235))
+    Rd = R.cpu().double()
+    assert (Rd.transpose(-1, -2) @ Rd - torch.eye(3, dtype=torch.float64)).abs().max() < 5e-6
+    assert (torch.linalg.det(Rd) - 1).abs().max() < 5e-6
+    for b in range(B):
+        Ro = orc.sample_matrix_fisher(A[b], n, gen)
+        tol = 5.0 / (n ** 0.5)                                          # entries of R are bounded by 1: sigma <= 1 / sqrt(n)
+        assert (Rd[b].mean(0) - Ro.mean(0)).abs().max() < tol
+        t_dev, t_orc = (Rd[b] * A[b]).sum((-1, -2)), (Ro * A[b]).sum((-1, -2))
+        assert abs(float(t_dev.mean() - t_orc.mean())) < 5.0 * float(t_orc.std()) * (2.0 / n) ** 0.5
+        assert abs(float(t_dev.std() / t_orc.std()) - 1.0) < 0.03
 
 
 def test_geodesic_metrics():

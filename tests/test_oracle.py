@@ -173,3 +173,19 @@ def test_geodesic_metric_against_live_reference():
     est = orc.random_rotations(50, gen, torch.float64)
     gt = orc.random_rotations(50 * 5, gen, torch.float64).reshape(50, 5, 3, 3)
     assert torch.equal(orc.min_geodesic_distance_rotmats(est, gt), ru.min_geodesic_distance_rotmats(est, gt))
+
+
+def test_matrix_fisher_sampler_against_importance_sampling():
+    """oracle.sample_matrix_fisher (utils/fisher.py:117-207 restated) draws from p(R) ~ exp(tr(A^T R)): its sample mean of R
+    and of tr(A^T R) match self-normalised importance sampling from the uniform distribution."""
+    gen = torch.Generator().manual_seed(3)
+    U, V = orc.random_rotations(2, gen, torch.float64)
+    A = U @ torch.diag(torch.tensor([3.0, 2.0, -1.0], dtype=torch.float64)) @ V.T
+    R = orc.sample_matrix_fisher(A, 100000, gen)
+    assert (R.transpose(1, 2) @ R - torch.eye(3, dtype=torch.float64)).abs().max() < 1e-12 and (torch.linalg.det(R) - 1).abs().max() < 1e-12
+    Ru = orc.random_rotations(400000, gen, torch.float64)
+    w = torch.exp((Ru * A).sum((-1, -2)))
+    mean_is = (w[:, None, None] * Ru).sum(0) / w.sum()
+    tr_is = (w * (Ru * A).sum((-1, -2))).sum() / w.sum()
+    assert (R.mean(0) - mean_is).abs().max() < 0.02
+    assert abs(float((R * A).sum((-1, -2)).mean() - tr_is)) < 0.05
