@@ -38,6 +38,9 @@ namespace {
 #ifndef RNF_T4_FHFMA
 #define RNF_T4_FHFMA 0
 #endif
+#ifndef RNF_T4_ROTATE_ISSUER
+#define RNF_T4_ROTATE_ISSUER 1
+#endif
 #ifndef RNF_T4_NP
 #define RNF_T4_NP 2              // mixture pairs evaluated together
 #endif
@@ -152,8 +155,15 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
   const int warp = tid >> 5, lane = tid & 31;
   const int tile = warp >> 2;                        // 0..3
   const int rowi = (warp & 3) * 32 + lane;           // row inside the tile = TMEM lane
-  const bool elected = rowi == 0;                    // counts the tile's consumption of weight pieces, refills them
-  const bool issuer_warp = (warp & 3) == 0;          // warp-uniform: issues this tile's MMAs
+  // The warp that issues a tile's MMAs (and whose lane 0 counts / refills weight pieces) sits in a different lane quarter,
+  // i.e. on a different scheduler, for every tile: the ~1.2 k instructions of MMA issue per tile-layer are spread over the
+  // four schedulers instead of making scheduler 0's warps the ones every hand-over waits for.
+#if RNF_T4_ROTATE_ISSUER
+  const bool issuer_warp = (warp & 3) == (tile & 3);  // warp-uniform
+#else
+  const bool issuer_warp = (warp & 3) == 0;
+#endif
+  const bool elected = issuer_warp && lane == 0;
   const uint32_t bars = smem_u32(smem + kOffBar);
 
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kOffMisc);
