@@ -184,6 +184,37 @@ def test_edge_cases():
     assert (before - after).abs().max() > 1e-4
 
 
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("kw", [dict(layers=1), dict(layers=2), dict(layers=3, frequent_permute=1), dict(layers=2, dist="noflow"),
+                                dict(layers=1, first_affine=0), dict(layers=2, condition=1, feature_dim=16, last_affine=1)],
+                         ids=["one_layer", "two_layers", "frequent_permute", "noflow", "mobius_only_1", "cond_small"])
+def test_short_and_odd_stacks(kw, mode):
+    """Stacks that stress the weight pipeline of the persistent kernels (1 or 2 Mobius layers: every refill targets the layer
+    in flight; no Mobius layer at all) in all three directions of use: rows forward, rows inverse, grid."""
+    cfg = orc.simple_config(**kw)
+    m = seeded_product_flow(cfg, 5).cuda().eval()
+    o = orc.OracleFlow(cfg, {k: v.cpu() for k, v in m.state_dict().items()}, torch.float64)
+    gen = torch.Generator().manual_seed(2)
+    N = 700                                                              # 6 tiles: groups of four with idle tiles
+    R = orc.random_rotations(N, gen)
+    F = orc.feature_dim_of(cfg)
+    B = 3
+    feat = torch.relu(torch.randn(B, F, generator=gen)) if F else None
+    rows = None if feat is None else feat.repeat_interleave((N + B - 1) // B, 0)[:N]
+    with torch.no_grad():
+        Rg, lg = m(R.cuda(), None if rows is None else rows.cuda(), mlp_mode=mode)
+        Ro, lo = o.forward(R, rows)
+        assert (Rg.cpu().double() - Ro).abs().max() < 1e-5 and rel(lg.cpu().double(), lo) < 1e-4
+        Ri, li = m.inverse(Rg, None if rows is None else rows.cuda(), mlp_mode=mode)
+        assert (Ri.cpu() - R).abs().max() < 2e-3 and (li + lg).abs().max() < 2e-3       # bisection resolution
+        grid = orc.healpix_grid(1).float()
+        out = m.grid_log_prob(grid.cuda(), None if feat is None else feat.cuda(), return_logp=True, mlp_mode=mode)
+        Bn = 1 if feat is None else B
+        _, l64 = o.forward(grid.double().repeat(Bn, 1, 1), None if feat is None else feat.double().repeat_interleave(grid.shape[0], 0))
+        assert rel(out["logp"].cpu().double().reshape(-1), l64) < 1e-4
+        assert torch.equal(out["argmax"].cpu(), out["logp"].argmax(dim=-1).cpu())
+
+
 def test_healpix_grid_on_device():
     z = np.load(f"{GOLDEN}/healpix_grid.npz")
     for level in (0, 1, 2):
