@@ -215,6 +215,36 @@ def test_short_and_odd_stacks(kw, mode):
         assert torch.equal(out["argmax"].cpu(), out["logp"].argmax(dim=-1).cpu())
 
 
+def test_grid_pass_is_cuda_graph_capturable():
+    """The whole grid evaluation (per-image conditioning, fused flow kernel, combine) is asynchronous on the current stream
+    with no host synchronisation: it can be captured once in a CUDA graph and replayed on new features."""
+    g = golden("s_symsol")
+    m = _product(g)
+    grid = orc.healpix_grid(1).float().cuda()
+    off = orc.random_rotations(1, torch.Generator().manual_seed(1))[0].cuda()
+    feat = g.feat.cuda().clone()
+    with torch.no_grad():
+        eager = m.grid_log_prob(grid, feat, offset=off, return_logp=True)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            m.grid_log_prob(grid, feat, offset=off, return_logp=True)          # warm-up on the capture stream
+        torch.cuda.current_stream().wait_stream(side)
+        with torch.cuda.graph(graph):
+            out = m.grid_log_prob(grid, feat, offset=off, return_logp=True)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out["logp"], eager["logp"]) and torch.equal(out["argmax"], eager["argmax"])
+        feat.copy_(torch.relu(torch.randn(feat.shape, generator=torch.Generator().manual_seed(9))).cuda())   # new inputs, same graph
+        graph.replay()
+        torch.cuda.synchronize()
+        fresh = m.grid_log_prob(grid, feat, offset=off, return_logp=True)
+        assert torch.equal(out["logp"], fresh["logp"]) and torch.equal(out["argmax"], fresh["argmax"])
+        assert not torch.equal(fresh["logp"], eager["logp"])
+
+
 def test_healpix_grid_on_device():
     z = np.load(f"{GOLDEN}/healpix_grid.npz")
     for level in (0, 1, 2):
