@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--images", type=int, default=int(os.environ.get("RNF_BENCH_IMAGES", "8")))
     ap.add_argument("--level", type=int, default=5)
     ap.add_argument("--mode", default=os.environ.get("RNF_BENCH_MODE", ""))
-    ap.add_argument("--cpu-sample", type=int, default=20000)
+    ap.add_argument("--cpu-sample", type=int, default=160000)      # ~10 s of host work per pass at ~16 k rot/s on 16 cores
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
