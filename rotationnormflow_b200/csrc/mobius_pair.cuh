@@ -189,16 +189,22 @@ __device__ __forceinline__ void probe_pairs(float zr, float zv, const float* prm
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     const f32x2 alt = fma2(at[j], bc(-1.0f), bc(1.5707963267948966f));
-    float a_[2], b_[2], th_[2];
+    // Wrap to [0, 2 pi) with sign bits instead of two compare / select pairs.  phi = angle of (|hr|, |hv|) from the r axis;
+    // its complement c = pi/2 - phi is picked directly (asin or its complement), then
+    //   pi - theta_[0,pi] = pi/2 + copysign(c, hr)            (hr >= 0: pi - phi, hr < 0: phi)        =: v in [0, pi]
+    //   theta             = pi - copysign(v, hv)              (hv >= 0: pi - v,   hv < 0: pi + v)
+    // which is atan2(hv, hr) wrapped exactly (tests/test_fastmath.py).
+    float a_[2], b_[2], u_[2], v_[2];
     upk(at[j], a_[0], a_[1]);
     upk(alt, b_[0], b_[1]);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      float p = fabsf(hv_[2 * j + i]) > fabsf(hr_[2 * j + i]) ? b_[i] : a_[i];   // first octant pair
-      p = hr_[2 * j + i] < 0.0f ? kPi - p : p;                         // angle in [0, pi] of (|hv|, hr)
-      th_[i] = hv_[2 * j + i] < 0.0f ? kTwoPi - p : p;
+      const float c = fabsf(hv_[2 * j + i]) > fabsf(hr_[2 * j + i]) ? a_[i] : b_[i];
+      u_[i] = copysignf(c, hr_[2 * j + i]);
     }
-    Fs = fma2(pk(prm[8 * j + 6], prm[8 * j + 7]), pk(th_[0], th_[1]), Fs);
+    upk(add2(pk(u_[0], u_[1]), bc(1.5707963267948966f)), v_[0], v_[1]);
+    const f32x2 th = fma2(pk(copysignf(v_[0], hv_[2 * j]), copysignf(v_[1], hv_[2 * j + 1])), bc(-1.0f), bc(kPi));
+    Fs = fma2(pk(prm[8 * j + 6], prm[8 * j + 7]), th, Fs);
   }
 }
 

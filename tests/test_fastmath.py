@@ -130,3 +130,18 @@ def test_sincos_2pi_accuracy():
     C = np.where(q == 0, cs, np.where(q == 1, -sn, np.where(q == 2, -cs, sn)))
     assert np.abs(S - np.sin(t.astype(np.float64))).max() < 1.2e-7
     assert np.abs(C - np.cos(t.astype(np.float64))).max() < 1.2e-7
+
+
+def test_sign_bit_quadrant_logic_of_the_probe():
+    """probe_pairs wraps the angle with two copysigns: theta = pi - copysign(pi/2 + copysign(c, hr), hv), c = the complement of
+    the first-quadrant angle.  Float64 emulation against atan2 wrapped to [0, 2 pi) over the whole circle."""
+    t = np.random.default_rng(0).uniform(0, 2 * np.pi, 200000)
+    hr, hv = np.cos(t), np.sin(t)
+    ay, ax = np.abs(hv), np.abs(hr)
+    at = np.arcsin(np.minimum(ay, ax))
+    c = np.where(ay > ax, at, np.pi / 2 - at)
+    v = np.pi / 2 + np.copysign(c, hr)
+    th = np.pi - np.copysign(v, hv)
+    ref = np.arctan2(hv, hr)
+    ref = np.where(ref >= 0, ref, ref + 2 * np.pi)
+    assert np.abs(th - ref).max() < 1e-14
