@@ -39,6 +39,15 @@ def _worker_body(rank, world, port, q):
     ridx, rmx, rlme = orc.grid_reduce(logp)
     ok = torch.equal(out[1], ridx) and torch.equal(out[0], rmx) and \
         float((rdist.log_normaliser(out[0], out[2], G) - rlme).abs().max()) < 1e-5
+    # the same collective with the spread numerators riding along ([B,4] instead of [B,3])
+    samples = orc.random_rotations(G, gen)
+    gt = orc.random_rotations(B * 2, gen).reshape(B, 2, 3, 3)
+    prod = torch.einsum("gij,bkij->bgk", samples.double(), gt.double())
+    d = torch.acos(torch.clip((prod.max(-1).values - 1.0) / 2.0, -1.0, 1.0))
+    e_part = torch.exp(part.double() - m[:, None].double())
+    out4 = rdist.all_merge(m, part.argmax(1) + b, e_part.sum(1).float(), sn=(e_part * d[:, b:e]).sum(1).float())
+    want = orc.spread(logp, samples, gt)
+    ok = ok and torch.equal(out4[1], ridx) and float(((out4[3].double() / out4[2].double()) - want).abs().max()) < 1e-5
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
