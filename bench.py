@@ -131,6 +131,31 @@ def cpu_leg(cfg, state_dict, sample_rows, threads, level=5, seed=123, repeats=1)
     return sample_rows / min(times), times
 
 
+def eager_gpu_leg(cfg, state_dict, dev, rows=500000, level=5, seed=321):
+    """The practical incumbent: the reference's op sequence (oracle port, explicit Jacobian) in eager PyTorch on
+    the B200, one 500 000-rotation chunk as at eval.py:445, features materialised per row as at eval.py:450.  Reported
+    next to the CPU number; a baseline, not part of `value`."""
+    from oracle import rnf_oracle as orc
+    o = orc.OracleFlow(cfg, state_dict, torch.float32, explicit_jacobian=True, device=dev)
+    G = 72 * 8 ** level
+    gen = torch.Generator().manual_seed(seed)
+    start = int(torch.randint(0, G - rows, (1,), generator=gen))
+    grid = orc.healpix_grid(level, start, start + rows).to(dev)
+    off = orc.random_rotations(1, gen)[0].to(dev)
+    feat = torch.relu(torch.randn(1, orc.feature_dim_of(cfg), generator=gen)).to(dev)
+    times = []
+    for _ in range(3):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        samples = grid @ off
+        rows_f = feat.repeat(rows, 1)
+        _, ldj = o.forward(samples, rows_f)
+        _ = torch.argmax(ldj).item()
+        torch.cuda.synchronize(dev)
+        times.append(time.perf_counter() - t0)
+    return rows / min(times)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -330,6 +355,14 @@ def main():
         "check": {"argmax0": int(res[1][0]), "log_norm0": float(res[2][0])},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            del flush
+            torch.cuda.empty_cache()
+            v_eager = eager_gpu_leg(cfg, {k: t.detach() for k, t in flow.state_dict().items()}, dev)
+            line["eager_torch_gpu_baseline"] = {"value": v_eager, "unit": UNIT, "kind": "port",
+                                                "sample": "one 500 000-rotation chunk x 1 image (eval.py:445), oracle port of flow/*.py as eager PyTorch ops on the same B200, best of 3"}
+        except Exception as e:  # a baseline only: never fail the bench line over it
+            line["eager_torch_gpu_baseline"] = {"value": None, "error": repr(e)[:200]}
         threads = os.cpu_count() or 1
         v, times = cpu_leg(cfg, {k: t.cpu() for k, t in flow.state_dict().items()}, args.cpu_sample, threads, repeats=2)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",

@@ -153,7 +153,7 @@ def _mobius_prep(sd, prefix, x, y, feature, K):
 
 def _explicit_ldj(x, r, v, pi, w):
     """The reference's literal Jacobian construction (flow/mobiusflow.py:104-125); equals log sum pi_k f_k."""
-    eye = torch.eye(3, dtype=x.dtype)
+    eye = torch.eye(3, dtype=x.dtype, device=x.device)
     z_w = x[:, None, :] - w
     n = z_w.norm(dim=-1)
     u = z_w / n[..., None]
@@ -166,7 +166,7 @@ def _explicit_ldj(x, r, v, pi, w):
 
 
 def _assemble(p, c0, c1, c2):
-    out = torch.empty((c0.shape[0], 3, 3), dtype=c0.dtype)
+    out = torch.empty((c0.shape[0], 3, 3), dtype=c0.dtype, device=c0.device)
     out[:, :, p[0]] = c0
     out[:, :, p[1]] = c1
     out[:, :, p[2]] = c2
@@ -249,7 +249,7 @@ def quat_affine(W, R, with_ldj=True):
     length = q.norm(dim=-2, keepdim=True)
     Rt = quaternion_to_matrix((q / length).reshape(-1, 4))
     if not with_ldj:
-        return Rt, torch.zeros(R.shape[0], dtype=R.dtype)
+        return Rt, torch.zeros(R.shape[0], dtype=R.dtype, device=R.device)
     return Rt, det4(W).abs().log() - 4 * length.reshape(-1).log()
 
 
@@ -269,7 +269,7 @@ def rot_weight(M):
 
 def affine_matrix(sd, prefix, kind, feature, inverse):
     """The 4x4 matrix a layer applies in the requested direction, and whether it carries a log-det."""
-    eye = torch.eye(4, dtype=next(iter(sd.values())).dtype).unsqueeze(0)
+    eye = torch.eye(4, dtype=next(iter(sd.values())).dtype, device=next(iter(sd.values())).device).unsqueeze(0)
     if kind == "aff_u":
         W = sd[prefix + "mat"]
     elif kind == "aff_lu":
@@ -293,24 +293,27 @@ def affine_matrix(sd, prefix, kind, feature, inverse):
 class OracleFlow:
     """``OracleFlow(cfg, state_dict)``; ``forward/inverse(rotation[N,3,3], feature[N,F]|None) -> (rotation, ldj)``."""
 
-    def __init__(self, cfg, state_dict, dtype=torch.float32, explicit_jacobian=False):
+    def __init__(self, cfg, state_dict, dtype=torch.float32, explicit_jacobian=False, device="cpu"):
+        """``device``: "cpu" (the oracle proper).  bench.py's incumbent leg passes a CUDA device to time the same eager
+        torch op sequence the reference would run on the GPU -- a baseline, never the product path."""
         self.cfg = cfg
         self.dtype = dtype
+        self.device = torch.device(device)
         self.K = cfg.segments
         self.plan = layer_plan(cfg)
         for k in self.plan:
             if k is None or str(k).startswith("unsupported") or k == "aff_clu":
                 raise NotImplementedError(f"layer kind {k!r} is outside the hot-path scope (SURVEY.md section 2 rows 5,7)")
-        self.sd = {k: torch.as_tensor(v).detach().to("cpu").to(dtype if torch.as_tensor(v).is_floating_point() else torch.as_tensor(v).dtype)
+        self.sd = {k: torch.as_tensor(v).detach().to(self.device).to(dtype if torch.as_tensor(v).is_floating_point() else torch.as_tensor(v).dtype)
                    for k, v in state_dict.items()}
         self.explicit = explicit_jacobian
 
     def _run(self, R, feature, inverse):
         cfg = self.cfg
-        R = R.detach().to("cpu", self.dtype)
-        feature = None if (feature is None or not cfg.condition) else feature.detach().to("cpu", self.dtype)
+        R = R.detach().to(self.device, self.dtype)
+        feature = None if (feature is None or not cfg.condition) else feature.detach().to(self.device, self.dtype)
         rows = permute_rows(cfg, self.plan, inverse)
-        ldjs = torch.zeros(R.shape[0], dtype=self.dtype)
+        ldjs = torch.zeros(R.shape[0], dtype=self.dtype, device=self.device)
         order = range(len(self.plan) - 1, -1, -1) if inverse else range(len(self.plan))
         for i in order:
             kind, pre, p = self.plan[i], f"layers.{i}.", PERMUTE_TABLE[rows[i]]
