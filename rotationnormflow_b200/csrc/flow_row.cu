@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
       if (!INV) {
         const float S_th = hsum(S_th2), S_f = hsum(S_f2);
         const float inv_sp = rcp_nr(S_sp);
-        circle_point_fast(P.r, P.v, S_th * inv_sp, nx);
+        circle_point_fast(P.r, P.v, mixture_angle(S_th, inv_sp), nx);
         ldj += log_fast(S_f * inv_sp);
       } else {
         // target angle of the given column in its own frame (flow/mobiusflow.py:157-167); ~pi by construction

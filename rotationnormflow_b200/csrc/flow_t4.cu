@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
       float nx[3], nz[3];
       const float S_sp = hsum(S_sp2), S_th = hsum(S_th2), S_f = hsum(S_f2);
       const float inv_sp = rcp_nr(S_sp);
-      circle_point_fast(P.r, P.v, S_th * inv_sp, nx);
+      circle_point_fast(P.r, P.v, mixture_angle(S_th, inv_sp), nx);
       ldj += log_fast(S_f * inv_sp);
       cross3(nx, y, nz);
       normalize3_fast(nz);

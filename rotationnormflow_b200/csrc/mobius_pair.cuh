@@ -7,8 +7,8 @@
 // the SFU operations (ex2, lg2, sqrt, rcp), min / max and the selects stay scalar.  56 -> ~37 instructions per component.
 //
 // Column layout of one pair (the host permutes the fc_last rows accordingly, engine._last_layer_perm_pairs): 8 consecutive
-// accumulator columns  (t_a, t_b, wx_a, wx_b, wy_a, wy_b, wz_a, wz_b)  with t = logit * log2(e) (the factor is folded into
-// the weights), so that a tcgen05.ld vector delivers every packed operand as an aligned register pair.
+// accumulator columns  (t_a, t_b, wx_a, wx_b, wy_a, wy_b, wz_a, wz_b)  with t = logit * log2(e) and w = 0.7 * centre (both factors are
+// folded into the weights), so that a tcgen05.ld vector delivers every packed operand as an aligned register pair.
 // Prepared parameters of a pair (inverse direction, kept in TMEM for the bisection):
 //   (-alpha'_a, -alpha'_b, -beta'_a, -beta'_b, 1 - |w'_a|^2, 1 - |w'_b|^2, weight_a, weight_b).
 #pragma once
@@ -71,14 +71,39 @@ __device__ __forceinline__ f32x2 asin_unit2(f32x2 m) {
   return fma2(mul2(p, s), m, m);
 }
 
-// NP pairs of mixture components, stage by stage.  raw[8 NP]: accumulator columns in the pair layout above.
-// FWD: accumulates (sum w, sum w theta, sum w f) as packed partial sums (a-components in the low, b in the high word).
-// !FWD: accumulates sum w and overwrites raw with the prepared parameters.
+// atan on the half-angle range of the forward direction: |q| <= tan(asin 0.7) = 0.9802 (see mixture_pairs).
+// atan(q) = q + q s P(s), s = q^2, P of degree 7 (minimax fit of the absolute error, tools/fit_atan_half.py: 5.6e-9 exact,
+// 6.1e-8 in fp32 Horner form, tests/test_fastmath.py).
+__device__ __forceinline__ f32x2 atan_half2(f32x2 q) {
+  const f32x2 s = mul2(q, q);
+  f32x2 p = bc(0.0028766694f);
+  p = fma2(p, s, bc(-0.01609694f));
+  p = fma2(p, s, bc(0.04260853f));
+  p = fma2(p, s, bc(-0.07486252f));
+  p = fma2(p, s, bc(0.10627319f));
+  p = fma2(p, s, bc(-0.14198953f));
+  p = fma2(p, s, bc(0.1999194f));
+  p = fma2(p, s, bc(-0.33333054f));
+  return fma2(mul2(p, s), q, q);
+}
+
+// NP pairs of mixture components, stage by stage.  raw[8 NP]: accumulator columns in the pair layout above; the centre rows
+// arrive PRE-SCALED by 0.7 (engine.pack_mobius_tc), so with (a', b') = 0.7 (w.r, w.v) and u = 1 + |w| = 1 + |(a', b')| / 0.7
+// the squashed centre of flow/mobiusflow.py:72 is w' = (a', b') / u.
+// FWD: the evaluation point is the moving column itself, z = (zr, 0) with zr = -|x|.  Everything is carried SCALED BY u, which
+// removes the reciprocal of u altogether:
+//     D = u (z - w') = (zr u - a', -b'),   |D|^2 = u^2 |z - w'|^2,   f = (1 - |w'|^2) / |z - w'|^2 = (u^2 - |(a',b')|^2) / |D|^2
+//     H = u h = (f D_r - a', -(f b' + b'))
+// h is a unit vector in the left half plane (|w'| < 0.7: within +-2 asin 0.7 of the angle pi), so its wrapped
+// angle is theta = pi - psi with tan(psi / 2) = h_v / (1 - h_r) = H_v / (u - H_r): ONE division, no octant selects, and
+//     sum_k w_k theta_k = pi sum_k w_k + 2 sum_k w_k atan(q_k),   q_k = (f b' + b') / (u - H_r)  (= -tan(psi_k / 2)).
+// Accumulates (sum w, sum w atan q, sum w f) as packed partial sums (a-components in the low, b in the high word).
+// !FWD: accumulates sum w and overwrites raw with the prepared parameters (-alpha', -beta', 1 - |w'|^2, weight).
 template <int NP, bool FWD>
-__device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv, float* raw, f32x2& S_sp, f32x2& S_th, f32x2& S_f) {
-  f32x2 sp[NP], nal[NP], nbe[NP], omw[NP];
+__device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv, float* raw, f32x2& S_sp, f32x2& S_at, f32x2& S_f) {
+  f32x2 sp[NP], ap[NP], bp[NP], bb[NP], n2[NP], u[NP], rt[NP];
   {
-    f32x2 t[NP], e[NP], a[NP], b[NP], n2[NP], rt[NP], big[NP], small[NP], ns[NP];
+    f32x2 t[NP], e[NP], big[NP], small[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       t[j] = pk(raw[8 * j], raw[8 * j + 1]);
@@ -87,9 +112,10 @@ __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       const f32x2 wx = pk(raw[8 * j + 2], raw[8 * j + 3]), wy = pk(raw[8 * j + 4], raw[8 * j + 5]), wz = pk(raw[8 * j + 6], raw[8 * j + 7]);
-      a[j] = fma2(wz, bc(P.r[2]), fma2(wy, bc(P.r[1]), mul2(wx, bc(P.r[0]))));
-      b[j] = fma2(wz, bc(P.v[2]), fma2(wy, bc(P.v[1]), mul2(wx, bc(P.v[0]))));
-      n2[j] = fma2(b[j], b[j], mul2(a[j], a[j]));
+      ap[j] = fma2(wz, bc(P.r[2]), fma2(wy, bc(P.r[1]), mul2(wx, bc(P.r[0]))));
+      bp[j] = fma2(wz, bc(P.v[2]), fma2(wy, bc(P.v[1]), mul2(wx, bc(P.v[0]))));
+      bb[j] = mul2(bp[j], bp[j]);
+      n2[j] = fma2(ap[j], ap[j], bb[j]);
       RNF_MAP2(rt[j], n2[j], sqrt_approx);
     }
 #pragma unroll
@@ -97,13 +123,7 @@ __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv
       const f32x2 ope = add2(e[j], bc(1.0f));
       RNF_MAP2(big[j], ope, lg2_approx);
       small[j] = mul2(e[j], fma2(e[j], bc(-0.7213475204444817f), bc(1.4426950408889634f)));
-    }
-#pragma unroll
-    for (int j = 0; j < NP; ++j) {
-      const f32x2 opr = add2(rt[j], bc(1.0f));
-      f32x2 rc;
-      RNF_MAP2(rc, opr, rcp_approx);
-      ns[j] = mul2(rc, bc(-0.7f));                      // -0.7 / (1 + |w|)   (flow/mobiusflow.py:72, sign folded)
+      u[j] = fma2(rt[j], bc(1.4285714285714286f), bc(1.0f));            // 1 + |w|
     }
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
@@ -111,58 +131,55 @@ __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv
       upk(t[j], tl, th); upk(e[j], el, eh); upk(big[j], bl, bh); upk(small[j], sl, sh);
       const float vl = el < 0.0078125f ? sl : bl, vh = eh < 0.0078125f ? sh : bh;
       sp[j] = pk(tl > 28.853900817779268f ? tl : vl, th > 28.853900817779268f ? th : vh);
-      nal[j] = mul2(ns[j], a[j]);
-      nbe[j] = mul2(ns[j], b[j]);
-      omw[j] = fma2(neg2(mul2(ns[j], ns[j])), n2[j], bc(1.0f));        // 1 - |w'|^2 = 1 - (0.7 / (1 + |w|))^2 |w|^2
     }
   }
   if (FWD) {
-    f32x2 f[NP], hr[NP], hv[NP], mn[NP];
+    f32x2 f[NP], q[NP];
+    const f32x2 nzr = bc(-zr);
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-      // forward direction: the evaluation point is the moving column itself, z = -|x| r exactly (v is orthogonal to x), so
-      // zv = 0 and z - w' has the in-plane components (zr - alpha', -beta')
-      const f32x2 dr = add2(nal[j], bc(zr)), dv = nbe[j];
-      const f32x2 dd = fma2(dv, dv, mul2(dr, dr));
+      // written without a single negation of a packed value (ptxas turns those into two LOP3 each): Dn = -D_r, Hn = -H_r
+      const f32x2 Dn = fma2(nzr, u[j], ap[j]);
+      const f32x2 DD = fma2(Dn, Dn, bb[j]);
+      // u^2 - |(a',b')|^2 with |(a',b')| = rt:  1 + (2 / 0.7) rt + (1 / 0.49 - 1) rt^2  -- all terms positive
+      const f32x2 num = fma2(fma2(rt[j], bc(1.0408163265306123f), bc(2.857142857142857f)), rt[j], bc(1.0f));
       f32x2 rc;
-      RNF_MAP2(rc, dd, rcp_approx);
-      f[j] = mul2(omw[j], rc);
-      hr[j] = fma2(f[j], dr, nal[j]);
-      hv[j] = fma2(f[j], dv, nbe[j]);
-      float hrl, hrh, hvl, hvh;
-      upk(hr[j], hrl, hrh);
-      upk(hv[j], hvl, hvh);
-      mn[j] = pk(fminf(fabsf(hvl), fabsf(hrl)), fminf(fabsf(hvh), fabsf(hrh)));
+      RNF_MAP2(rc, DD, rcp_approx);
+      f[j] = mul2(num, rc);
+      const f32x2 Hn = fma2(f[j], Dn, ap[j]);
+      const f32x2 Hvn = fma2(f[j], bp[j], bp[j]);
+      const f32x2 den = add2(u[j], Hn);
+      f32x2 rcd;
+      RNF_MAP2(rcd, den, rcp_approx);
+      q[j] = mul2(Hvn, rcd);
     }
     f32x2 at[NP];
 #pragma unroll
-    for (int j = 0; j < NP; ++j) at[j] = asin_unit2(mn[j]);
+    for (int j = 0; j < NP; ++j) at[j] = atan_half2(q[j]);
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-      // angle of h from the negative r axis; hr < 0 always in the forward direction, so theta = pi - sign(hv) * that
-      const f32x2 alt = fma2(at[j], bc(-1.0f), bc(1.5707963267948966f));
-      float al_, ah_, bl_, bh_, hvl, hvh, hrl, hrh;
-      upk(at[j], al_, ah_);
-      upk(alt, bl_, bh_);
-      upk(hv[j], hvl, hvh);
-      upk(hr[j], hrl, hrh);
-      const float ul = fabsf(hvl) > fabsf(hrl) ? bl_ : al_, uh = fabsf(hvh) > fabsf(hrh) ? bh_ : ah_;
-      const f32x2 th = fma2(pk(copysignf(ul, hvl), copysignf(uh, hvh)), bc(-1.0f), bc(kPi));
       S_sp = add2(S_sp, sp[j]);
-      S_th = fma2(sp[j], th, S_th);
+      S_at = fma2(sp[j], at[j], S_at);
       S_f = fma2(sp[j], f[j], S_f);
     }
   } else {
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
+      f32x2 rc;
+      RNF_MAP2(rc, u[j], rcp_approx);
+      const f32x2 nal = mul2(neg2(ap[j]), rc), nbe = mul2(neg2(bp[j]), rc);
+      const f32x2 omw = fma2(neg2(mul2(rc, rc)), n2[j], bc(1.0f));      // 1 - |w'|^2
       S_sp = add2(S_sp, sp[j]);
-      upk(nal[j], raw[8 * j], raw[8 * j + 1]);
-      upk(nbe[j], raw[8 * j + 2], raw[8 * j + 3]);
-      upk(omw[j], raw[8 * j + 4], raw[8 * j + 5]);
+      upk(nal, raw[8 * j], raw[8 * j + 1]);
+      upk(nbe, raw[8 * j + 2], raw[8 * j + 3]);
+      upk(omw, raw[8 * j + 4], raw[8 * j + 5]);
       upk(sp[j], raw[8 * j + 6], raw[8 * j + 7]);
     }
   }
 }
+
+// wrapped mixture angle theta' = sum_k w_k theta_k / sum_k w_k from the forward sums of mixture_pairs
+__device__ __forceinline__ float mixture_angle(float S_at, float inv_sp) { return fmaf(2.0f * S_at, inv_sp, kPi); }
 
 // Bisection probe of NP prepared pairs at the in-plane point (zr, zv) = (cos t, sin t): accumulates sum_k weight_k theta_k(z).
 // Full-circle atan2: during the bisection z sweeps [pi/2, 3pi/2] and h may land anywhere (flow/mobiusflow.py:226-245).

@@ -28,6 +28,7 @@ TC_WEIGHT_SCALE = 1.0    # fp16 hi/lo weight planes are stored unscaled (biases 
 MOB_TC_FLOATS = (3 * (2 * 8192 + 64 * 32) + (2 * 32768 + 256 * 32) + 1024 + 64 * 32) // 4   # kTcImageBytes / 4 in csrc/tc_common.cuh
 
 LOG2E = 1.4426950408889634
+CENTRE_SCALE = 0.7       # folded into the centre rows of fc_last in the tensor-core image (pack_mobius_tc)
 
 _MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC, "tc_row": _cabi.RNF_MLP_TC_ROW}
 
@@ -156,6 +157,10 @@ def pack_mobius_tc(cond_sd: dict) -> np.ndarray:
     W4, b4 = _np(cond_sd["fc_last.weight"]).copy(), _np(cond_sd["fc_last.bias"]).copy()
     W4[:K_SEGMENTS] *= np.float32(LOG2E)
     b4[:K_SEGMENTS] *= np.float32(LOG2E)
+    # ... and the centre rows the factor 0.7 of flow/mobiusflow.py:72 (w <- 0.7 w / (1 + |w|)): the kernels work with
+    # (a', b') = 0.7 (w.r, w.v) and u = 1 + |(a', b')| / 0.7, which saves the forward direction a reciprocal (mobius_pair.cuh)
+    W4[K_SEGMENTS:] *= np.float32(CENTRE_SCALE)
+    b4[K_SEGMENTS:] *= np.float32(CENTRE_SCALE)
     perm = _last_layer_perm_pairs(K_SEGMENTS)
     hi, lo = _split_fp16(W4[perm])
     parts += [_umma_k_major_sw128(hi).view(np.float32), _umma_k_major_sw128(lo).view(np.float32),

@@ -84,7 +84,7 @@ def test_packed_asin_polynomial_accuracy():
     """mobius_pair.cuh takes the angle of the unit vector h from its nearer axis as asin(min(|h.r|, |h.v|)) (no division):
     float32 Horner emulation of the polynomial read back from the header, against asin on [0, 1/sqrt 2]."""
     src = open(os.path.join(ROOT, "rotationnormflow_b200", "csrc", "mobius_pair.cuh")).read()
-    body = src[src.index("f32x2 asin_unit2"):src.index("// NP pairs of mixture components")]
+    body = src[src.index("f32x2 asin_unit2"):src.index("// atan on the half-angle range")]
     co = [float(v) for v in re.findall(r"bc\((-?[0-9.e-]+)f\)", body)]          # highest power first
     assert len(co) == 7
     m = np.linspace(0, 0.70711, 1_000_001).astype(np.float32)
@@ -145,3 +145,67 @@ def test_sign_bit_quadrant_logic_of_the_probe():
     ref = np.arctan2(hv, hr)
     ref = np.where(ref >= 0, ref, ref + 2 * np.pi)
     assert np.abs(th - ref).max() < 1e-14
+
+
+def test_half_angle_atan_polynomial_and_identity():
+    """mixture_pairs (forward) takes theta = pi + 2 atan(q), q = -(tan of half the angle of h from the negative r axis) =
+    -h_v / (1 - h_r), |q| <= tan(asin 0.7): float32 Horner emulation of atan_half2 read back from the header, and the
+    half-angle identity against atan2 wrapped to [0, 2 pi) over the left half plane."""
+    src = open(os.path.join(ROOT, "rotationnormflow_b200", "csrc", "mobius_pair.cuh")).read()
+    body = src[src.index("f32x2 atan_half2"):src.index("// NP pairs of mixture components")]
+    co = [float(v) for v in re.findall(r"bc\((-?[0-9.e-]+)f\)", body)]          # highest power first
+    assert len(co) == 8
+    qmax = np.tan(np.arcsin(0.7))
+    q = np.linspace(-qmax, qmax, 2_000_001).astype(np.float32)
+    s = (q.astype(np.float64) * q).astype(np.float32)
+    p = np.full_like(s, np.float32(co[0]))
+    for c in co[1:]:
+        p = _fma32(p, s, np.float32(c))
+    ps = (p.astype(np.float64) * s).astype(np.float32)
+    res = (ps.astype(np.float64) * q + q).astype(np.float32)
+    assert np.abs(res.astype(np.float64) - np.arctan(q.astype(np.float64))).max() < 7e-8
+    psi = np.linspace(-2 * np.arcsin(0.7), 2 * np.arcsin(0.7), 100001)
+    hr, hv = -np.cos(psi), np.sin(psi)                                   # unit vector within +-2 asin(0.7) of the angle pi
+    ref = np.arctan2(hv, hr)
+    ref = np.where(ref >= 0, ref, ref + 2 * np.pi)
+    qq = -hv / (1 - hr)
+    assert np.abs(qq).max() <= qmax * (1 + 1e-12)
+    assert np.abs(np.pi + 2 * np.arctan(qq) - ref).max() < 1e-14
+
+
+def test_scaled_forward_component_algebra():
+    """The u-scaled forward evaluation of mixture_pairs (no reciprocal of u = 1 + |w|) against the textbook formulas
+    (flow/mobiusflow.py:17-24,72,94-99), float64, random centres of any magnitude.  The half-angle step uses |h| = 1, i.e.
+    a unit moving column; a column of norm 1 + eps moves the angle by O(eps), like the asin form it replaces."""
+    rng = np.random.default_rng(0)
+    n = 100000
+    sc = 10 ** rng.uniform(-3, 2, n)
+    a, b = rng.standard_normal(n) * sc, rng.standard_normal(n) * sc
+    zr = -np.ones(n)
+    nrm = np.sqrt(a * a + b * b)
+    s = 0.7 / (1 + nrm)
+    al, be = s * a, s * b
+    dr, dv = zr - al, -be
+    f = (1 - al * al - be * be) / (dr * dr + dv * dv)
+    th = np.arctan2(f * dv - be, f * dr - al)
+    th = np.where(th >= 0, th, th + 2 * np.pi)
+    ap, bp = 0.7 * a, 0.7 * b
+    rt = np.sqrt(ap * ap + bp * bp)
+    u = 1 + rt / 0.7
+    Dn = -zr * u + ap
+    DD = Dn * Dn + bp * bp
+    num = (rt * (1 / 0.49 - 1) + 2 / 0.7) * rt + 1
+    f2 = num / DD
+    Hn = f2 * Dn + ap
+    q = (f2 * bp + bp) / (u + Hn)
+    assert (np.abs(f2 - f) / f).max() < 1e-12
+    assert np.abs(np.pi + 2 * np.arctan(q) - th).max() < 1e-12
+    zr = -(1 + rng.uniform(-3e-7, 3e-7, n))                             # fp32-rounded column norm
+    dr = zr - al
+    f = (1 - al * al - be * be) / (dr * dr + dv * dv)
+    th = np.arctan2(f * dv - be, f * dr - al)
+    th = np.where(th >= 0, th, th + 2 * np.pi)
+    Dn = -zr * u + ap
+    f2 = num / (Dn * Dn + bp * bp)
+    q = (f2 * bp + bp) / (u + f2 * Dn + ap)
+    assert (np.abs(f2 - f) / f).max() < 1e-12 and np.abs(np.pi + 2 * np.arctan(q) - th).max() < 1e-6

@@ -160,7 +160,7 @@ def test_tensor_core_image_is_the_reference_mlp():
         base = 8 * (comp // 2) + (comp % 2)
         assert abs(out[base] - ref[comp] * engine.LOG2E) < 2e-6 * scale
         got_w = out[[base + 2, base + 4, base + 6]]
-        assert np.abs(got_w - ref[K + 3 * comp: K + 3 * comp + 3]).max() < 2e-6 * scale
+        assert np.abs(got_w - engine.CENTRE_SCALE * ref[K + 3 * comp: K + 3 * comp + 3]).max() < 2e-6 * scale
     perm = engine._last_layer_perm_pairs(K)
     assert sorted(perm.tolist()) == list(range(4 * K))
 
