@@ -41,6 +41,9 @@ namespace {
 #ifndef RNF_T4_ROTATE_ISSUER
 #define RNF_T4_ROTATE_ISSUER 1
 #endif
+#ifndef RNF_T4_WAIT_BAR
+#define RNF_T4_WAIT_BAR 1        // long waits: one polling warp per tile, the others in a named barrier
+#endif
 #ifndef RNF_T4_NP
 #define RNF_T4_NP 2              // mixture pairs evaluated together
 #endif
@@ -223,6 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
   const uint32_t bias_hid_d = umma_desc_lo_ns(smem_u32(smem + kOffW + 16384)), bias_last_d = umma_desc_lo_ns(smem_u32(smem + kOffLastW + 65536));
   const uint32_t aux_blk_d = umma_desc_lo_ns(smem_u32(smem + kOffAux + kAuxFirst));
   const int bar_tile = 1 + tile;                     // named barrier of the tile's 128 threads
+  const int bar_wait = 9 + tile;                     // ... and the one its non-issuing warps sleep in during a GEMM round trip
   const uint32_t bar_mma = bars + 8 * (BAR_MMA + tile);
   uint32_t par_mma = 0, par_w = 0;
   int64_t step = 0;
@@ -239,6 +243,25 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
     mbar_wait(bar_mma, par_mma);
     par_mma ^= 1;
     tc_fence_after();
+  };
+  // The same for a wait that is expected to be LONG (the dependent GEMM round trips of the chain): only the issuing warp polls
+  // the mbarrier; the other three warps of the tile sleep in a hardware named barrier, which costs no issue slots.  (ncu on the
+  // all-poll version: the YIELD / SYNCS.TRYWAIT / BRA loop is 12.7 % of all executed warp instructions -- a try_wait suspends
+  // for ~100 cycles only.)  The issuer issued the MMAs it waits for, so its tcgen05 fences order them for the other warps.
+  auto wait_mma_long = [&]() {
+#if RNF_T4_WAIT_BAR
+    if (issuer_warp) {
+      mbar_wait(bar_mma, par_mma);
+      tc_fence_before();
+      named_arrive(bar_wait, 128);
+    } else {
+      named_bar(bar_wait, 128);
+    }
+    par_mma ^= 1;
+    tc_fence_after();
+#else
+    wait_mma();
+#endif
   };
 
   for (int64_t item = 0; item < my_items; ++item) {
@@ -364,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
           __syncwarp();
         }
         TRACE(2 + 3 * l);
-        wait_mma();
+        wait_mma_long();
         TRACE(3 + 3 * l);
         // a piece is dead once ALL tiles' GEMM that reads it has completed: the last tile to get here refills it
         if (elected) {
@@ -418,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
 #else
         float buf0[16], buf1[16];
         if (c == 2) TRACE(30);                        // 30 / 31: how long chunk 2's MMAs keep the tile waiting
-        wait_mma();
+        if (c == 0) wait_mma_long(); else wait_mma();  // chunks 1..3 ran under the previous chunk's arithmetic: no spinning
         if (c == 2) TRACE(31);
         TRACE(14 + c);
         W4_DONE();

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+RNF_TEST_MODES=tc,tc_x2 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --timeout 60 -k "forward_parity or short_and_odd or grid_log_prob or spread or edge or capturable" > gpurun_out/r02_pytest4.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/r02_pytest4.log
+MODE=tc PREFIX=w_ bash tools/ab2.sh 2>&1 | tee gpurun_out/r02_ab4.log
+MODE=tc_x2 PREFIX=w_ bash tools/ab2.sh 2>&1 | tee -a gpurun_out/r02_ab4.log
