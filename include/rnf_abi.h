@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RNF_ABI_VERSION 8
+#define RNF_ABI_VERSION 7
 
 /* error codes */
 #define RNF_OK 0
@@ -44,8 +44,6 @@ extern "C" {
 #define RNF_MLP_TC 1      /* tcgen05 tensor cores, error-compensated split operands, FP32 accumulate: forward / grid with four
                              tiles per SM and the activations in tensor memory (csrc/flow_t4.cu), inverse as RNF_MLP_TC_ROW */
 #define RNF_MLP_TC_ROW 2  /* same arithmetic, two tiles per SM, activations through shared memory (csrc/flow_row.cu)   */
-#define RNF_MLP_TC_X2 3   /* as RNF_MLP_TC with two warps (owner + helper) per tile and lane quarter: forward / grid in
-                             csrc/flow_t4x.cu (1024 threads per SM), inverse as RNF_MLP_TC_ROW                          */
 
 /*
  * One entry per layer, in module order (index i == `layers.{i}` of the reference state dict).

@@ -11,14 +11,13 @@ import threading
 
 from . import build as _build
 
-ABI_VERSION = 8
+ABI_VERSION = 7
 
 RNF_LAYER_MOBIUS = 0
 RNF_LAYER_AFFINE = 1
 RNF_MLP_FP32 = 0
 RNF_MLP_TC = 1
 RNF_MLP_TC_ROW = 2
-RNF_MLP_TC_X2 = 3
 
 
 class LayerDesc(C.Structure):

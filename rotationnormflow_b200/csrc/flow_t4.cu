@@ -41,6 +41,12 @@ namespace {
 #ifndef RNF_T4_ROTATE_ISSUER
 #define RNF_T4_ROTATE_ISSUER 1
 #endif
+#ifndef RNF_T4_SPLIT_MASK
+#define RNF_T4_SPLIT_MASK 1
+#endif
+#ifndef RNF_T4_EARLY_W
+#define RNF_T4_EARLY_W 1         // look at the next GEMM's weight barrier right after issuing the current one
+#endif
 #ifndef RNF_T4_WAIT_BAR
 #define RNF_T4_WAIT_BAR 1        // long waits: one polling warp per tile, the others in a named barrier
 #endif
@@ -117,6 +123,17 @@ __device__ __forceinline__ void relu_split_pair(float x0, float x1, uint32_t& hi
       "}\n"
       : "=f"(d0), "=f"(d1)
       : "r"(hi), "f"(x0), "f"(x1));
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
+#elif RNF_T4_SPLIT_MASK
+  // The fp16 truncation of x, back in fp32, is x with its low 13 mantissa bits cleared: two LOP3 on the (half idle) ALU pipe
+  // instead of two HADD2.F32 on the FMA pipe, which is the busiest pipe of this kernel (tools/pipe_rate.cu: every one of these
+  // instructions costs 2 cycles per warp on its pipe).  Differs from the converted-back value only where fp16 is subnormal
+  // (x < 6.1e-5: the sum hi + lo is then off by < 6e-8 absolute) and above the fp16 range (x > 65504 saturates at 65504
+  // instead of 2 x 65504); negative x: hi = 0 and x - (x & mask) <= 0 -> lo = 0.
+  asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float m0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u), m1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+  float d0, d1;
+  upk(sub2(pk(x0, x1), pk(m0, m1)), d0, d1);
   asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
 #else
   asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
@@ -229,6 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
   const int bar_wait = 9 + tile;                     // ... and the one its non-issuing warps sleep in during a GEMM round trip
   const uint32_t bar_mma = bars + 8 * (BAR_MMA + tile);
   uint32_t par_mma = 0, par_w = 0;
+  bool w_ready = false;                              // issuing warp: the next GEMM's weight piece is known to have landed
   int64_t step = 0;
   int mob_cur = 0;
   constexpr uint32_t kIdesc = umma_idesc(128, 64);
@@ -368,8 +386,10 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
       for (int l = 0; l < 4; ++l) {
         if (issuer_warp) {
           TRACE(20 + 2 * l);                          // 20 .. 29: time spent waiting for the weight pieces
-          if (l == 0) mbar_wait(bars + 8 * (BAR_AUX_FULL + abuf), (uint32_t)((step >> 1) & 1));
-          else mbar_wait(bars + 8 * (BAR_W_FULL + l - 1), (par_w >> (l - 1)) & 1u);
+          if (!w_ready) {
+            if (l == 0) mbar_wait(bars + 8 * (BAR_AUX_FULL + abuf), (uint32_t)((step >> 1) & 1));
+            else mbar_wait(bars + 8 * (BAR_W_FULL + l - 1), (par_w >> (l - 1)) & 1u);
+          }
           TRACE(21 + 2 * l);
           tc_fence_after();
           if (elect_one_sync()) {
@@ -385,6 +405,14 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
             umma_commit(bar_mma);
           }
           __syncwarp();
+#if RNF_T4_EARLY_W
+          // While this GEMM runs: one non-blocking look at the barrier of the NEXT GEMM's weights (W_{l+1}, then W4), so that the
+          // ~150-cycle mbarrier round trip of an already completed barrier is off the chain's critical path (timeline: 8 such
+          // waits per tile and layer).  Not a blocking wait: the piece may still belong to a slower tile's previous layer.
+          w_ready = mbar_test(bars + 8 * (BAR_W_FULL + l), (par_w >> l) & 1u);
+#else
+          w_ready = false;
+#endif
         }
         TRACE(2 + 3 * l);
         wait_mma_long();
@@ -403,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
       auto issue_chunk = [&](int c) {               // issuing warp only, right after the hand-over barrier
         if (c == 0) {
           TRACE(28);
-          mbar_wait(bars + 8 * (BAR_W_FULL + 3), (par_w >> 3) & 1u);
+          if (!w_ready) mbar_wait(bars + 8 * (BAR_W_FULL + 3), (par_w >> 3) & 1u);
           TRACE(29);
         }
         tc_fence_after();
@@ -415,6 +443,11 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
           umma_commit(bar_mma);
         }
         __syncwarp();
+#if RNF_T4_EARLY_W
+        if (c == 3) {                                  // next layer's fc_first block (aux buffer of step + 1)
+          w_ready = step + 1 < total_steps && mbar_test(bars + 8 * (BAR_AUX_FULL + (abuf ^ 1)), (uint32_t)(((step + 1) >> 1) & 1));
+        }
+#endif
       };
       if (issuer_warp) issue_chunk(0);
       f32x2 S_sp2 = 0ull, S_th2 = 0ull, S_f2 = 0ull;   // packed partial sums (even | odd components)

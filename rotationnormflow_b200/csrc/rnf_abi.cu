@@ -25,14 +25,13 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 long long* g_trace = nullptr;
 
-bool valid_mode(int m) { return m == RNF_MLP_FP32 || m == RNF_MLP_TC || m == RNF_MLP_TC_ROW || m == RNF_MLP_TC_X2; }
+bool valid_mode(int m) { return m == RNF_MLP_FP32 || m == RNF_MLP_TC || m == RNF_MLP_TC_ROW; }
 
 }  // namespace
 
 namespace rnf {
 cudaError_t launch_flow_row(const FlowArgs& a, bool inverse, int sm_count, cudaStream_t st);
 cudaError_t launch_flow_t4(const FlowArgs& a, int sm_count, cudaStream_t st);
-cudaError_t launch_flow_t4x(const FlowArgs& a, int sm_count, cudaStream_t st);
 bool flow_tc_supported(const rnf_flow* f);
 }  // namespace rnf
 
@@ -165,7 +164,6 @@ static int run_rows(rnf_flow* f, bool inverse, const float* R_in, int64_t N, con
     // RNF_MLP_TC: four tiles per SM in the forward direction (flow_t4.cu); the bisection of the inverse needs its prepared
     // parameters resident in tensor memory and runs in the two-tile kernel (flow_row.cu), as does everything in RNF_MLP_TC_ROW
     if (mlp_mode == RNF_MLP_TC && !inverse) e = rnf::launch_flow_t4(a, f->sm_count, (cudaStream_t)stream);
-    else if (mlp_mode == RNF_MLP_TC_X2 && !inverse) e = rnf::launch_flow_t4x(a, f->sm_count, (cudaStream_t)stream);
     else e = rnf::launch_flow_row(a, inverse, f->sm_count, (cudaStream_t)stream);
   } else {
     a.n_tiles = (N + rnf::kV1Threads - 1) / rnf::kV1Threads;
@@ -248,7 +246,6 @@ int rnf_grid_logprob_spread(rnf_flow* f, const float* grid_dev, int64_t G, int64
     a.tiles_per_image = (G + 127) / 128;
     a.n_tiles = a.tiles_per_image * B;
     if (mlp_mode == RNF_MLP_TC) e = rnf::launch_flow_t4(a, f->sm_count, (cudaStream_t)stream);
-    else if (mlp_mode == RNF_MLP_TC_X2) e = rnf::launch_flow_t4x(a, f->sm_count, (cudaStream_t)stream);
     else e = rnf::launch_flow_row(a, false, f->sm_count, (cudaStream_t)stream);
   } else {
     a.tiles_per_image = (G + rnf::kV1Threads - 1) / rnf::kV1Threads;

@@ -30,7 +30,7 @@ MOB_TC_FLOATS = (3 * (2 * 8192 + 64 * 32) + (2 * 32768 + 256 * 32) + 1024 + 64 *
 LOG2E = 1.4426950408889634
 CENTRE_SCALE = 0.7       # folded into the centre rows of fc_last in the tensor-core image (pack_mobius_tc)
 
-_MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC, "tc_row": _cabi.RNF_MLP_TC_ROW, "tc_x2": _cabi.RNF_MLP_TC_X2}
+_MODES = {"fp32": _cabi.RNF_MLP_FP32, "tc": _cabi.RNF_MLP_TC, "tc_row": _cabi.RNF_MLP_TC_ROW}
 
 
 def default_mlp_mode() -> str:

@@ -21,7 +21,7 @@ from rotationnormflow_b200.fisher import fisher_constants
 
 pytestmark = pytest.mark.gpu
 
-MODES = [m for m in os.environ.get("RNF_TEST_MODES", "fp32,tc,tc_row,tc_x2").split(",") if m]
+MODES = [m for m in os.environ.get("RNF_TEST_MODES", "fp32,tc,tc_row").split(",") if m]
 
 
 def _mode_available(mode):

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+RNF_TEST_MODES=tc timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -s --timeout 60 -k "forward_parity or short_and_odd or grid_log_prob or spread or edge or capturable" > gpurun_out/r02_pytest6.log 2>&1; echo "pytest rc=$?"
+tail -3 gpurun_out/r02_pytest6.log; grep "/tc\] fwd" gpurun_out/r02_pytest6.log | tail -4
+MODE=tc PREFIX=y_ bash tools/ab2.sh 2>&1 | tee gpurun_out/r02_ab6.log
