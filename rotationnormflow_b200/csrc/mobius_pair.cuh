@@ -14,10 +14,6 @@
 #pragma once
 #include "mobius_fast.cuh"
 
-#ifndef RNF_ATAN_DEG
-#define RNF_ATAN_DEG 7
-#endif
-
 namespace rnf {
 
 typedef unsigned long long f32x2;   // two fp32 in a 64-bit register pair: low word = component a, high word = component b
@@ -80,15 +76,6 @@ __device__ __forceinline__ f32x2 asin_unit2(f32x2 m) {
 // 6.1e-8 in fp32 Horner form, tests/test_fastmath.py).
 __device__ __forceinline__ f32x2 atan_half2(f32x2 q) {
   const f32x2 s = mul2(q, q);
-#if RNF_ATAN_DEG == 6
-  f32x2 p = bc(-0.004723619f);                          // degree 6: 3.9e-8 exact, 9.9e-8 in fp32 Horner form
-  p = fma2(p, s, bc(0.024251247f));
-  p = fma2(p, s, bc(-0.059338886f));
-  p = fma2(p, s, bc(0.098946035f));
-  p = fma2(p, s, bc(-0.14009611f));
-  p = fma2(p, s, bc(0.19967842f));
-  p = fma2(p, s, bc(-0.3333194f));
-#else
   f32x2 p = bc(0.0028766694f);
   p = fma2(p, s, bc(-0.01609694f));
   p = fma2(p, s, bc(0.04260853f));
@@ -97,7 +84,6 @@ __device__ __forceinline__ f32x2 atan_half2(f32x2 q) {
   p = fma2(p, s, bc(-0.14198953f));
   p = fma2(p, s, bc(0.1999194f));
   p = fma2(p, s, bc(-0.33333054f));
-#endif
   return fma2(mul2(p, s), q, q);
 }
 
