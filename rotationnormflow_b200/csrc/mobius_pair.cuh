@@ -90,13 +90,13 @@ __device__ __forceinline__ f32x2 atan_half2(f32x2 q) {
 // NP pairs of mixture components, stage by stage.  raw[8 NP]: accumulator columns in the pair layout above; the centre rows
 // arrive PRE-SCALED by 0.7 (engine.pack_mobius_tc), so with (a', b') = 0.7 (w.r, w.v) and u = 1 + |w| = 1 + |(a', b')| / 0.7
 // the squashed centre of flow/mobiusflow.py:72 is w' = (a', b') / u.
-// FWD: the evaluation point is the moving column itself, z = (zr, 0) with zr = -|x|.  Everything is carried SCALED BY u, which
-// removes the reciprocal of u altogether:
-//     D = u (z - w') = (zr u - a', -b'),   |D|^2 = u^2 |z - w'|^2,   f = (1 - |w'|^2) / |z - w'|^2 = (u^2 - |(a',b')|^2) / |D|^2
-//     H = u h = (f D_r - a', -(f b' + b'))
-// h is a unit vector in the left half plane (|w'| < 0.7: within +-2 asin 0.7 of the angle pi), so its wrapped
-// angle is theta = pi - psi with tan(psi / 2) = h_v / (1 - h_r) = H_v / (u - H_r): ONE division, no octant selects, and
-//     sum_k w_k theta_k = pi sum_k w_k + 2 sum_k w_k atan(q_k),   q_k = (f b' + b') / (u - H_r)  (= -tan(psi_k / 2)).
+// FWD: the evaluation point is the moving column itself, z = (zr, 0) with zr = -|x|, a point of the unit circle, on which the
+// map of flow/mobiusflow.py:17-24 is the disk automorphism h = (z - w') / (1 - conj(w') z) (complex notation), so that
+//     arg h = 2 arg(z - w') - arg z = 2 arg(z - w') - pi.
+// Scaled by u (no reciprocal of u):  D = u (z - w') = (zr u - a', -b') =: (-Dn, -b'),  Dn > 0.3 u,  arg(z - w') = pi + atan(b' / Dn):
+//     theta = pi + 2 atan(q),  q = b' / Dn,  |q| < tan(asin 0.7);   sum_k w_k theta_k = pi sum_k w_k + 2 sum_k w_k atan(q_k)
+// -- one division, no octant selects, and the angle does not wait for f.  The log-det term needs
+//     f = (1 - |w'|^2) / |z - w'|^2 = (u^2 - |(a',b')|^2) / |D|^2,   |D|^2 = Dn^2 + b'^2.
 // Accumulates (sum w, sum w atan q, sum w f) as packed partial sums (a-components in the low, b in the high word).
 // !FWD: accumulates sum w and overwrites raw with the prepared parameters (-alpha', -beta', 1 - |w'|^2, weight).
 template <int NP, bool FWD>
@@ -138,20 +138,16 @@ __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv
     const f32x2 nzr = bc(-zr);
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-      // written without a single negation of a packed value (ptxas turns those into two LOP3 each): Dn = -D_r, Hn = -H_r
+      // written without a single negation of a packed value (ptxas turns those into two LOP3 each): Dn = -D_r > 0
       const f32x2 Dn = fma2(nzr, u[j], ap[j]);
       const f32x2 DD = fma2(Dn, Dn, bb[j]);
       // u^2 - |(a',b')|^2 with |(a',b')| = rt:  1 + (2 / 0.7) rt + (1 / 0.49 - 1) rt^2  -- all terms positive
       const f32x2 num = fma2(fma2(rt[j], bc(1.0408163265306123f), bc(2.857142857142857f)), rt[j], bc(1.0f));
-      f32x2 rc;
+      f32x2 rc, rcd;
       RNF_MAP2(rc, DD, rcp_approx);
+      RNF_MAP2(rcd, Dn, rcp_approx);
       f[j] = mul2(num, rc);
-      const f32x2 Hn = fma2(f[j], Dn, ap[j]);
-      const f32x2 Hvn = fma2(f[j], bp[j], bp[j]);
-      const f32x2 den = add2(u[j], Hn);
-      f32x2 rcd;
-      RNF_MAP2(rcd, den, rcp_approx);
-      q[j] = mul2(Hvn, rcd);
+      q[j] = mul2(bp[j], rcd);
     }
     f32x2 at[NP];
 #pragma unroll

@@ -149,8 +149,8 @@ def test_sign_bit_quadrant_logic_of_the_probe():
 
 def test_half_angle_atan_polynomial_and_identity():
     """mixture_pairs (forward) takes theta = pi + 2 atan(q), q = -(tan of half the angle of h from the negative r axis) =
-    -h_v / (1 - h_r), |q| <= tan(asin 0.7): float32 Horner emulation of atan_half2 read back from the header, and the
-    half-angle identity against atan2 wrapped to [0, 2 pi) over the left half plane."""
+    -h_v / (1 - h_r) (= b' / Dn in the kernel's variables), |q| <= tan(asin 0.7): float32 Horner emulation of atan_half2 read
+    back from the header, and the half-angle identity against atan2 wrapped to [0, 2 pi) over the left half plane."""
     src = open(os.path.join(ROOT, "rotationnormflow_b200", "csrc", "mobius_pair.cuh")).read()
     body = src[src.index("f32x2 atan_half2"):src.index("// NP pairs of mixture components")]
     co = [float(v) for v in re.findall(r"bc\((-?[0-9.e-]+)f\)", body)]          # highest power first
@@ -196,8 +196,8 @@ def test_scaled_forward_component_algebra():
     DD = Dn * Dn + bp * bp
     num = (rt * (1 / 0.49 - 1) + 2 / 0.7) * rt + 1
     f2 = num / DD
-    Hn = f2 * Dn + ap
-    q = (f2 * bp + bp) / (u + Hn)
+    q = bp / Dn                                                         # arg h = 2 arg(z - w') - arg z on the unit circle
+    assert np.abs(q - (f2 * bp + bp) / (u + f2 * Dn + ap)).max() < 1e-12  # == -h_v / (1 - h_r), the half-angle tangent of h itself
     assert (np.abs(f2 - f) / f).max() < 1e-12
     assert np.abs(np.pi + 2 * np.arctan(q) - th).max() < 1e-12
     zr = -(1 + rng.uniform(-3e-7, 3e-7, n))                             # fp32-rounded column norm
@@ -207,5 +207,5 @@ def test_scaled_forward_component_algebra():
     th = np.where(th >= 0, th, th + 2 * np.pi)
     Dn = -zr * u + ap
     f2 = num / (Dn * Dn + bp * bp)
-    q = (f2 * bp + bp) / (u + f2 * Dn + ap)
+    q = bp / Dn
     assert (np.abs(f2 - f) / f).max() < 1e-12 and np.abs(np.pi + 2 * np.arctan(q) - th).max() < 1e-6
