@@ -575,6 +575,52 @@ def run_sampling_config(ctx, mode, steps, warmup, n_img=64, n_per=1_000_000):
     return rec, (cfg, flow)
 
 
+def run_dropin(ctx, mode, rows=500_000):
+    """The literal drop-in calls: eval.py:444-453 scores a 500 000-rotation chunk with
+    `flow(samples, feature.repeat(len(samples), 1))`; agent.py:240-261 calls `flow.inverse(base, feature.repeat...)`.  The
+    repeated feature tensor (4 GB at F=2048) is built inside the timed region, as the reference does; the flow de-duplicates
+    it on the device (csrc/dedup.cu, one streaming read) and reads the 4-byte run count back (N > the optimistic capacity)."""
+    from oracle import rnf_oracle as orc
+    from rotationnormflow_b200 import engine, grid as rgrid
+    out = {}
+    for F in (2048, 512):
+        cfg, flow = build_flow("symsol", feature_dim=F)
+        flow = flow.to(ctx.dev).eval()
+        chunk = rgrid.healpix_grid(5, 0, rows, device=ctx.dev)
+        off = orc.random_rotations(1, torch.Generator().manual_seed(9))[0].to(ctx.dev)
+        f1 = torch.relu(torch.randn(1, F, generator=torch.Generator().manual_seed(10))).to(ctx.dev)
+        with torch.no_grad():
+            def fwd():
+                samples = chunk @ off
+                feats = f1.repeat(rows, 1)
+                _, ldj = flow(samples, feats, mlp_mode=mode)
+                return torch.argmax(ldj)
+
+            def inv():
+                feats = f1.repeat(rows, 1)
+                S, ldj = flow.inverse(chunk, feats, mlp_mode=mode)
+                return torch.argmax(-ldj)
+
+            def direct():                                            # the same chunk through the N1 API (no repeated features)
+                o = flow.grid_log_prob(chunk, f1, offset=off, mlp_mode=mode)
+                return o["argmax"]
+
+            ms_f = ctx.timed(fwd, 5, 3)
+            ms_i = ctx.timed(inv, 3, 2)
+            ms_d = ctx.timed(direct, 5, 3)
+            feats = f1.repeat(rows, 1)
+            ms_dd = ctx.timed(lambda: engine.dedup_rows(feats, engine.DEDUP_CAP), 5, 3)
+            del feats
+        out[f"F{F}"] = {"forward_rot_per_s": rows / (ms_f * 1e-3), "inverse_rot_per_s": rows / (ms_i * 1e-3),
+                        "grid_log_prob_same_chunk_rot_per_s": rows / (ms_d * 1e-3), "forward_ms": ms_f, "inverse_ms": ms_i,
+                        "dedup_ms": ms_dd, "dedup_read_GBps": rows * F * 4 / (ms_dd * 1e-3) / 1e9,
+                        "repeated_feature_bytes": rows * F * 4}
+        del flow, chunk
+        torch.cuda.empty_cache()
+    out["config"] = f"symsol.yml, one image, {rows}-rotation chunk of the level-5 grid; feature.repeat inside the timed region; L2 flushed between steps"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -622,6 +668,7 @@ def main():
         extra["3"] = {k: r3[k] for k in ("metric", "value", "ms_per_step", "config", "roofline", "e2e", "check")}
         r5, _ = run_grid_config(ctx, 5, mode, 2, 3, want_e2e=False)
         extra["5"] = {k: r5[k] for k in ("metric", "value", "ms_per_step", "config", "roofline")}
+        line["e2e_dropin"] = run_dropin(ctx, mode)
         extra["5"]["note"] = "one GPU scoring the whole 37.7 M grid: the N = 1 point of the strong-scaling series the default run measures under torchrun"
         line["configs"] = extra
     if ctx.rank == 0 and ctx.world == 1 and cfg_id == 2 and not args.no_cpu_baseline:

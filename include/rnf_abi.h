@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RNF_ABI_VERSION 7
+#define RNF_ABI_VERSION 8
 
 /* error codes */
 #define RNF_OK 0
@@ -106,6 +106,25 @@ int64_t rnf_flow_cond_floats(const rnf_flow* flow);
  *   feat_dev [B,F] float32 row-major  ->  cond_dev [B, rnf_flow_cond_floats()]
  */
 int rnf_flow_condition(rnf_flow* flow, const float* feat_dev, int64_t B, float* cond_dev, void* stream);
+
+/*
+ * The reference's calling convention: `feature [N,F]` row-aligned with the rotations, built by `.repeat` (agent.py:240-244,
+ * eval.py:450), i.e. long runs of identical rows.  rnf_dedup_rows recovers the run structure on the device, asynchronously:
+ *   idx_out_dev   [N]   int32: run number of every row (the feat_index_dev of rnf_flow_forward / _inverse), clamped to cap - 1
+ *   first_out_dev [cap] int32: first row of run b (entries >= count are 0)
+ *   count_out_dev [1]   int32: number of runs.  If it exceeds `cap` the per-image buffers sized by `cap` do not hold all
+ *                       images: the caller either reads it back and retries with a larger cap, or (stream capture) calls
+ *                       rnf_poison_if_overflow after the flow, which turns every log-det into NaN in that case.
+ *   workspace_dev : rnf_dedup_workspace_bytes(N) bytes.
+ * One streaming pass over the N x F floats (HBM-bound), a device-wide scan, a scatter: no host synchronisation.
+ * rnf_flow_condition_runs is rnf_flow_condition for the images (feat row first[b], b < *count_dev) of that structure.
+ */
+int64_t rnf_dedup_workspace_bytes(int64_t N);
+int rnf_dedup_rows(const float* feat_dev, int64_t N, int64_t F, int32_t* idx_out_dev, int32_t* first_out_dev, int64_t cap,
+                   int32_t* count_out_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
+int rnf_flow_condition_runs(rnf_flow* flow, const float* feat_dev, const int32_t* first_dev, const int32_t* count_dev,
+                            int64_t cap, float* cond_dev, void* stream);
+int rnf_poison_if_overflow(const int32_t* count_dev, int64_t cap, float* ldj_dev, int64_t N, void* stream);
 
 /*
  * Flow.forward (flow/flow.py:53-72) and Flow.inverse (flow/flow.py:74-92).

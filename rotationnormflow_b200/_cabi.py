@@ -11,7 +11,7 @@ import threading
 
 from . import build as _build
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 RNF_LAYER_MOBIUS = 0
 RNF_LAYER_AFFINE = 1
@@ -64,6 +64,10 @@ _SIGNATURES = {
     "rnf_flow_destroy": (None, [_P]),
     "rnf_flow_cond_floats": (_I64, [_P]),
     "rnf_flow_condition": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "rnf_dedup_workspace_bytes": (_I64, [_I64]),
+    "rnf_dedup_rows": (C.c_int, [_P, _I64, _I64, _P, _P, _I64, _P, _P, _I64, _P]),
+    "rnf_flow_condition_runs": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P]),
+    "rnf_poison_if_overflow": (C.c_int, [_P, _I64, _P, _I64, _P]),
     "rnf_flow_forward": (C.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _P, C.c_int, _P]),
     "rnf_flow_inverse_scratch_floats": (_I64, [_P, _I64]),
     "rnf_flow_inverse": (C.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P, C.c_int, _P]),

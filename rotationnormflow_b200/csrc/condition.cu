@@ -18,24 +18,34 @@ namespace {
 constexpr int BM = 64, BN = 64, BK = 16;
 
 // C[b, n] = sum_f feat[b, f] * Wf[n, f]      (both operands contiguous along f)
+// row_index (nullable): image m reads feature row row_index[m] (the first row of its run, csrc/dedup.cu) instead of row m;
+// count (nullable): device-side number of valid images -- rows at or beyond it are skipped (B is then only the capacity).
 __global__ void __launch_bounds__(256) hoist_gemm_kernel(const float* __restrict__ feat, const float* __restrict__ Wf,
                                                          int64_t B, int Ntot, int F, float* __restrict__ cond,
-                                                         int64_t stride, int n_mob, int n_aff) {
+                                                         int64_t stride, int n_mob, int n_aff, const int32_t* __restrict__ row_index,
+                                                         const int32_t* __restrict__ count) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Ws[BK][BN + 4];
   const int tid = threadIdx.x;
   const int64_t m0 = (int64_t)blockIdx.y * BM;
+  if (count != nullptr) {
+    const int64_t c = *count;
+    B = c < B ? c : B;
+  }
+  if (m0 >= B) return;                         // block-uniform
   const int n0 = blockIdx.x * BN;
   const int tm = (tid / 16) * 4, tn = (tid % 16) * 4;
   float acc[4][4] = {};
   const int lr = tid / 4, lk = (tid % 4) * 4;  // load row / k offset
+  const int64_t mrow = m0 + lr;
+  const int64_t src_row = (mrow < B && row_index != nullptr) ? (int64_t)__ldg(row_index + mrow) : mrow;
   for (int k0 = 0; k0 < F; k0 += BK) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int k = k0 + lk + i;
-      const int64_t m = m0 + lr;
+      const int64_t m = mrow;
       const int n = n0 + lr;
-      As[lk + i][lr] = (m < B && k < F) ? __ldg(feat + m * F + k) : 0.0f;
+      As[lk + i][lr] = (m < B && k < F) ? __ldg(feat + src_row * F + k) : 0.0f;
       Ws[lk + i][lr] = (n < Ntot && k < F) ? __ldg(Wf + (int64_t)n * F + k) : 0.0f;
     }
     __syncthreads();
@@ -93,8 +103,10 @@ __device__ void invert4(const float* A, float* inv) {
 
 // grid (B, n_aff), 64 threads: tail of ConditionalTransform(F, 16) for one (image, conditional affine layer).
 __global__ void __launch_bounds__(64) cond_affine_kernel(const float* __restrict__ caff, float* __restrict__ cond,
-                                                         int64_t stride, int n_mob, int n_aff, int is_rot) {
+                                                         int64_t stride, int n_mob, int n_aff, int is_rot,
+                                                         const int32_t* __restrict__ count) {
   const int64_t b = blockIdx.x;
+  if (count != nullptr && b >= *count) return;
   const int s = blockIdx.y;
   const int j = threadIdx.x;
   const float* w = caff + (int64_t)s * kCaffFloats;
@@ -145,20 +157,21 @@ __global__ void __launch_bounds__(64) cond_affine_kernel(const float* __restrict
 
 }  // namespace
 
-cudaError_t launch_condition(const rnf_flow* f, const float* feat, int64_t B, float* cond, cudaStream_t st) {
+cudaError_t launch_condition(const rnf_flow* f, const float* feat, int64_t B, float* cond, cudaStream_t st,
+                             const int32_t* row_index, const int32_t* count) {
   const rnf_model_desc& m = f->model;
   const int S = m.n_mobius_slots + m.n_affine_slots;
   if (S == 0 || B == 0) return cudaSuccess;
   const int Ntot = S * kH;
   dim3 grid((Ntot + BN - 1) / BN, (unsigned)((B + BM - 1) / BM));
   hoist_gemm_kernel<<<grid, 256, 0, st>>>(feat, f->weights_dev + m.wf_off, B, Ntot, m.F, cond, f->cond_floats,
-                                          m.n_mobius_slots, m.n_affine_slots);
+                                          m.n_mobius_slots, m.n_affine_slots, row_index, count);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (m.n_affine_slots > 0) {
     dim3 g2((unsigned)B, m.n_affine_slots);
     cond_affine_kernel<<<g2, 64, 0, st>>>(f->weights_dev + m.caff_off, cond, f->cond_floats, m.n_mobius_slots,
-                                          m.n_affine_slots, m.affine_is_rot);
+                                          m.n_affine_slots, m.affine_is_rot, count);
     e = cudaGetLastError();
   }
   return e;

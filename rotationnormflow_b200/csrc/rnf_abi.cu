@@ -76,6 +76,12 @@ int rnf_flow_create(const rnf_model_desc* model, const rnf_layer_desc* layers, c
       else { if (L.cond_slot != n_aff++) return fail(RNF_EINVAL, "layer %d: affine slots must be consecutive", i); }
     }
   }
+  {
+    int total_mobius = 0;
+    for (int i = 0; i < model->n_layers; ++i) total_mobius += layers[i].kind == RNF_LAYER_MOBIUS;
+    if (total_mobius > 64)
+      return fail(RNF_ESHAPE, "rnf_flow_create: %d Mobius layers; the kernels keep their weight-offset table in 64 shared-memory slots", total_mobius);
+  }
   if (n_mob != model->n_mobius_slots || n_aff != model->n_affine_slots)
     return fail(RNF_EINVAL, "slot counts (%d,%d) do not match the layer table (%d,%d)", model->n_mobius_slots,
                 model->n_affine_slots, n_mob, n_aff);
@@ -120,6 +126,38 @@ int rnf_flow_condition(rnf_flow* f, const float* feat_dev, int64_t B, float* con
   if (B < 0 || (B > 0 && (!feat_dev || !cond_dev))) return fail(RNF_EINVAL, "rnf_flow_condition: bad arguments");
   cudaError_t e = rnf::launch_condition(f, feat_dev, B, cond_dev, (cudaStream_t)stream);
   return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_flow_condition");
+}
+
+int64_t rnf_dedup_workspace_bytes(int64_t N) { return N > 0 ? (int64_t)rnf::dedup_scan_bytes(N) : 0; }
+
+int rnf_dedup_rows(const float* feat_dev, int64_t N, int64_t F, int32_t* idx_out_dev, int32_t* first_out_dev, int64_t cap,
+                   int32_t* count_out_dev, void* workspace_dev, int64_t workspace_bytes, void* stream) {
+  if (N < 0 || F <= 0 || cap <= 0) return fail(RNF_EINVAL, "rnf_dedup_rows: bad sizes");
+  if (N == 0) return RNF_OK;
+  if (N > 0x7fffffffLL) return fail(RNF_EINVAL, "rnf_dedup_rows: N=%lld rows exceed the int32 row index", (long long)N);
+  if (!feat_dev || !idx_out_dev || !first_out_dev || !count_out_dev || !workspace_dev) return fail(RNF_EINVAL, "rnf_dedup_rows: null buffer");
+  if (workspace_bytes < rnf_dedup_workspace_bytes(N)) return fail(RNF_EINVAL, "rnf_dedup_rows: workspace too small");
+  int sm = 148;
+  int rc = rnf_device_check(&sm);
+  if (rc != RNF_OK) return rc;
+  cudaError_t e = rnf::launch_dedup(feat_dev, N, F, idx_out_dev, first_out_dev, cap, count_out_dev, workspace_dev, (size_t)workspace_bytes,
+                                    sm, (cudaStream_t)stream);
+  return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_dedup_rows");
+}
+
+int rnf_flow_condition_runs(rnf_flow* f, const float* feat_dev, const int32_t* first_dev, const int32_t* count_dev, int64_t cap,
+                            float* cond_dev, void* stream) {
+  if (!f) return fail(RNF_EINVAL, "rnf_flow_condition_runs: null handle");
+  if (f->cond_floats == 0) return fail(RNF_ESTATE, "rnf_flow_condition_runs: the flow is unconditional");
+  if (cap <= 0 || !feat_dev || !first_dev || !count_dev || !cond_dev) return fail(RNF_EINVAL, "rnf_flow_condition_runs: bad arguments");
+  cudaError_t e = rnf::launch_condition(f, feat_dev, cap, cond_dev, (cudaStream_t)stream, first_dev, count_dev);
+  return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_flow_condition_runs");
+}
+
+int rnf_poison_if_overflow(const int32_t* count_dev, int64_t cap, float* ldj_dev, int64_t N, void* stream) {
+  if (N < 0 || !count_dev || (N > 0 && !ldj_dev)) return fail(RNF_EINVAL, "rnf_poison_if_overflow: bad arguments");
+  cudaError_t e = rnf::launch_poison(count_dev, cap, ldj_dev, N, (cudaStream_t)stream);
+  return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_poison_if_overflow");
 }
 
 static int run_rows(rnf_flow* f, bool inverse, const float* R_in, int64_t N, const float* cond, int64_t B,

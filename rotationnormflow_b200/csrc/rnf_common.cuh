@@ -89,7 +89,12 @@ cudaError_t launch_flow_v1(const FlowArgs& a, bool inverse, int sm_count, cudaSt
 cudaError_t launch_fisher_sample(const float* usv, int64_t B, int64_t n, unsigned long long seed, float* out, cudaStream_t st);
 cudaError_t launch_grid_combine(const float* part, int64_t tiles_per_image, int64_t B, int64_t g_index0, float* max_out,
                                 int64_t* argmax_out, float* sumexp_out, float* spread_num_out, cudaStream_t st);
-cudaError_t launch_condition(const rnf_flow* f, const float* feat, int64_t B, float* cond, cudaStream_t st);
+cudaError_t launch_condition(const rnf_flow* f, const float* feat, int64_t B, float* cond, cudaStream_t st,
+                             const int32_t* row_index = nullptr, const int32_t* count = nullptr);
+size_t dedup_scan_bytes(int64_t N);
+cudaError_t launch_dedup(const float* feat, int64_t N, int64_t F, int32_t* idx, int32_t* first, int64_t cap, int32_t* count, void* ws,
+                         size_t ws_bytes, int sm_count, cudaStream_t st);
+cudaError_t launch_poison(const int32_t* count, int64_t cap, float* ldj, int64_t N, cudaStream_t st);
 cudaError_t launch_healpix(int level, int64_t begin, int64_t end, float* out, cudaStream_t st);
 cudaError_t launch_min_geodesic(const float* est, const float* gt, int64_t B, int64_t K, float* out, cudaStream_t st);
 cudaError_t launch_fisher_logprob(const float* A9, const float* c, const float* R, int64_t N, int64_t rows_per_image, float* out,

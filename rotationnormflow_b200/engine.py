@@ -216,8 +216,30 @@ class LayerSpec:
         self.module = module
 
 
-def _sub_sd(module, prefix: str) -> dict:
-    return {k[len(prefix):]: v for k, v in module.state_dict().items() if k.startswith(prefix)}
+def conditioner_tensors(ct) -> dict:
+    """ConditionalTransform -> {state-dict key: tensor}, read through ATTRIBUTES: nn.DataParallel replicas (agent.py:22) carry
+    their weights as plain attributes, not as registered parameters, so state_dict() is empty there."""
+    out = {"fc_first.weight": ct.fc_first.weight, "fc_first.bias": ct.fc_first.bias,
+           "fc_last.weight": ct.fc_last.weight, "fc_last.bias": ct.fc_last.bias}
+    for j in (1, 3, 5):
+        out[f"layers.{j}.weight"], out[f"layers.{j}.bias"] = ct.layers[j].weight, ct.layers[j].bias
+    return out
+
+
+def layer_tensors(layer) -> list:
+    """Every tensor a layer's packed image depends on (attribute access, see conditioner_tensors)."""
+    if layer.kind == "mobius":
+        return list(conditioner_tensors(layer.conditioner).values())
+    if layer.kind in ("aff_c", "rot_c"):
+        return list(conditioner_tensors(layer.net).values())
+    if layer.kind == "aff_u":
+        return [layer.mat]
+    if layer.kind == "rot_u":
+        return [layer.rot]
+    if layer.kind == "aff_lu":
+        m = layer.mat
+        return [m.w_p, m.u_mask, m.l_mask, m.s_sign, m.l_eye, m.w_l, m.w_s, m.w_u]
+    return [t for t in list(layer.parameters()) + list(layer.buffers())]
 
 
 class Program:
@@ -256,7 +278,7 @@ class Program:
             d.w_off_tc = -1
             if s.kind == "mobius":
                 d.kind = _cabi.RNF_LAYER_MOBIUS
-                csd = _sub_sd(s.module, "conditioner.")
+                csd = conditioner_tensors(s.module.conditioner)
                 blk, wf = pack_mobius(csd, self.F if s.module.condition else 0)
                 d.w_off = push(blk)
                 d.w_off_tc = push(pack_mobius_tc(csd))
@@ -269,7 +291,7 @@ class Program:
                 d.has_ldj = 0 if s.kind.startswith("rot") else 1
                 if s.kind in ("aff_c", "rot_c"):
                     cond_kinds.add(s.kind)
-                    blk, wf = pack_cond_affine(_sub_sd(s.module, "net."), self.F)
+                    blk, wf = pack_cond_affine(conditioner_tensors(s.module.net), self.F)
                     d.cond_slot = n_aff
                     n_aff += 1
                     wf_aff.append(wf)
@@ -326,18 +348,44 @@ class Program:
             _cabi.check(self.lib.rnf_flow_condition(self.handle, C.c_void_p(feat.data_ptr()), B,
                                                     C.c_void_p(cond.data_ptr()), self._stream()))
         if self.rot_slots:
-            # ConditionRot (flow/rottrans.py:43-46,55-58): rot = U^T V with (U,S,V) = torch.svd(MLP(feature)+I);
-            # the SVD stays the very library call the reference makes (its sign convention defines the layer).
-            base = self.n_mob * HIDDEN
-            blk = cond[:, base: base + self.n_aff * AFF_FLOATS].view(B, self.n_aff, AFF_FLOATS)
-            M = blk[:, :, :16].reshape(B, self.n_aff, 4, 4)
-            # U^T V is NOT invariant under the sign freedom of an SVD (it maps to D U^T V D), so the LAPACK routine behind
-            # CPU torch.svd -- the one the golden vectors were minted with -- is used for determinism.
+            self._polar_factor(cond, B)
+        return cond
+
+    def _polar_factor(self, cond: torch.Tensor, B: int) -> None:
+        """ConditionRot (flow/rottrans.py:43-46,55-58): rot = U^T V with (U,S,V) = torch.svd(MLP(feature)+I), in place.
+
+        U^T V is NOT invariant under the sign freedom of an SVD (U -> U D, V -> V D maps it to D U^T V D), so the layer is
+        defined by the SVD routine the reference calls.  ``svd_backend()``: "device" (default) = torch.svd on the CUDA tensor, the
+        very call the reference makes when it runs on a GPU (cuSOLVER; asynchronous, no host round trip); "cpu" = LAPACK through
+        a host round trip, the convention of a reference run on the CPU (the golden vectors of tests/golden were minted there)."""
+        base = self.n_mob * HIDDEN
+        blk = cond[:, base: base + self.n_aff * AFF_FLOATS].view(B, self.n_aff, AFF_FLOATS)
+        M = blk[:, :, :16].reshape(B, self.n_aff, 4, 4)
+        if svd_backend() == "cpu":
             U, _, V = torch.svd(M.cpu())
             rot = (U.transpose(-1, -2) @ V).to(M.device)
-            blk[:, :, :16] = rot.reshape(B, self.n_aff, 16)
-            blk[:, :, AFF_INV:AFF_INV + 16] = rot.transpose(-1, -2).reshape(B, self.n_aff, 16)
+        else:
+            U, _, V = torch.svd(M)
+            rot = U.transpose(-1, -2) @ V
+        blk[:, :, :16] = rot.reshape(B, self.n_aff, 16)
+        blk[:, :, AFF_INV:AFF_INV + 16] = rot.transpose(-1, -2).reshape(B, self.n_aff, 16)
+
+    def condition_runs(self, feat: torch.Tensor, first: torch.Tensor, count: torch.Tensor, cap: int) -> torch.Tensor:
+        """Per-image constants for the runs found by ``dedup_rows`` (rnf_flow_condition_runs): image b < count reads feature
+        row first[b]; rows b >= count of the returned [cap, cond_floats] buffer are left untouched (never indexed)."""
+        # capacity rows beyond the run count are never indexed; for ConditionRot they still go through the batched SVD: keep them 0
+        alloc = torch.zeros if self.rot_slots else torch.empty
+        cond = alloc((cap, self.cond_floats), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.rnf_flow_condition_runs(self.handle, C.c_void_p(feat.data_ptr()), C.c_void_p(first.data_ptr()),
+                                                         C.c_void_p(count.data_ptr()), cap, C.c_void_p(cond.data_ptr()), self._stream()))
+        if self.rot_slots:
+            self._polar_factor(cond, cap)
         return cond
+
+    def poison_if_overflow(self, count: torch.Tensor, cap: int, ldj: torch.Tensor) -> None:
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.rnf_poison_if_overflow(C.c_void_p(count.data_ptr()), cap, C.c_void_p(ldj.data_ptr()), ldj.numel(), self._stream()))
 
     def run(self, R: torch.Tensor, cond, B: int, feat_index, rows_per_image: int, inverse: bool, mode: str):
         N = R.shape[0]
@@ -388,19 +436,31 @@ class Program:
         return mx, am, se, logp
 
 
-def dedup_rows(feature: torch.Tensor):
-    """Row-aligned ``feature [N,F]`` (built by ``.repeat`` at agent.py:240-244 / eval.py:450) ->
-    (unique consecutive rows [B,F], int32 row->image index [N] or None, rows_per_image)."""
-    N = feature.shape[0]
-    if N == 0:
-        return feature, None, 1
-    if feature.stride(0) == 0 or N == 1:
-        return feature[:1].contiguous(), None, N
-    neq = (feature[1:] != feature[:-1]).any(dim=1)
-    idx = torch.zeros(N, dtype=torch.int32, device=feature.device)
-    idx[1:] = torch.cumsum(neq, 0, dtype=torch.int32)
-    B = int(idx[-1].item()) + 1
-    if B == 1:
-        return feature[:1].contiguous(), None, N
-    first = torch.cat([torch.zeros(1, dtype=torch.int64, device=feature.device), torch.nonzero(neq).squeeze(1) + 1])
-    return feature[first].contiguous(), idx, 0
+DEDUP_CAP = 8192      # optimistic image capacity of the sync-free drop-in path (44 MB of per-image constants at most)
+
+
+def svd_backend() -> str:
+    """"device" (default) or "cpu": where ConditionRot / UnconditionRot evaluate torch.svd (RNF_SVD_BACKEND); see Program._polar_factor."""
+    v = os.environ.get("RNF_SVD_BACKEND", "device")
+    if v not in ("device", "cpu"):
+        raise ValueError(f"RNF_SVD_BACKEND={v!r}: expected 'device' or 'cpu'")
+    return v
+
+
+def dedup_rows(feature: torch.Tensor, cap: int):
+    """Row-aligned ``feature [N,F]`` (float32, contiguous, CUDA; built by ``.repeat`` at agent.py:240-244 / eval.py:450) ->
+    (idx int32 [N] row -> run number, first int32 [cap] first row of every run, count int32 [1] number of runs), all on the
+    device and asynchronous (rnf_dedup_rows: one streaming pass over the N x F floats, a scan, a scatter)."""
+    lib = _cabi.load()
+    N, F = feature.shape
+    dev = feature.device
+    idx = torch.empty((N,), dtype=torch.int32, device=dev)
+    first = torch.empty((cap,), dtype=torch.int32, device=dev)
+    count = torch.empty((1,), dtype=torch.int32, device=dev)
+    nbytes = int(lib.rnf_dedup_workspace_bytes(N))
+    ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _cabi.check(lib.rnf_dedup_rows(C.c_void_p(feature.data_ptr()), N, F, C.c_void_p(idx.data_ptr()), C.c_void_p(first.data_ptr()), cap,
+                                       C.c_void_p(count.data_ptr()), C.c_void_p(ws.data_ptr()), nbytes, st))
+    return idx, first, count

@@ -31,6 +31,20 @@ def get_flow(config):
     return Flow(config)
 
 
+class _NoProgramState:
+    """Mixin: the packed-program cache holds device pointers and a ctypes handle; it is rebuilt on demand and must not travel
+    through copy.deepcopy / pickle / torch.save of the module."""
+
+    def invalidate_cache(self):
+        """Forget the packed weights (needed only after writes that bypass autograd versioning, e.g. ``p.data.copy_()``)."""
+        self.__dict__.pop("_rnf_programs", None)
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_rnf_programs", None)
+        return state
+
+
 # ------------------------------------------------------------------------------------------------------
 # parameter containers (state-dict compatible with the reference modules)
 # ------------------------------------------------------------------------------------------------------
@@ -54,7 +68,7 @@ class ConditionalTransform(nn.Module):
         raise RuntimeError("ConditionalTransform is evaluated inside the fused CUDA kernels; call the owning layer / Flow")
 
 
-class _FusedLayer(nn.Module):
+class _FusedLayer(_NoProgramState, nn.Module):
     """Common per-layer protocol: ``layer(rotation, permute, feature)`` and ``layer.inverse(...)``."""
 
     kind = ""
@@ -184,8 +198,11 @@ class UnconditionRot(_FusedLayer):
         self.rot = nn.Parameter(torch.randn((1, 4, 4)) * 1e-3 + torch.eye(4).unsqueeze(0))
 
     def matrix(self):
+        # U^T V depends on the sign convention of the SVD routine (engine.Program._polar_factor): evaluated where the reference
+        # would evaluate it -- on the parameter's own device -- unless RNF_SVD_BACKEND=cpu asks for the LAPACK convention
         with torch.no_grad():
-            U, _, V = torch.svd(self.rot.detach().to("cpu"))
+            M = self.rot.detach()
+            U, _, V = torch.svd(M.to("cpu") if engine.svd_backend() == "cpu" else M)
             return U.transpose(-1, -2) @ V
 
 
@@ -266,14 +283,19 @@ def _perm_row(permute, layer) -> int:
 
 
 def _signature(layers) -> tuple:
-    sig = []
+    sig = [engine.svd_backend()]
     for l in layers:
-        for t in list(l.parameters()) + list(l.buffers()):
+        for t in engine.layer_tensors(l):
             sig.append((t.data_ptr(), t._version))
     return tuple(sig)
 
 
 def _program(owner, layers, perms, F, device) -> engine.Program:
+    """The packed program of (layers, perms) on ``device``, cached on the owning module.
+
+    The cache is keyed on (data_ptr, _version) of every weight tensor: optimizer steps, ``load_state_dict`` and any other in-place
+    write through the tensor itself are picked up.  Writes through ``.data`` (``p.data.copy_()``, some EMA / clipping code) do not
+    bump ``_version``: call ``Flow.invalidate_cache()`` after those."""
     cache = owner.__dict__.setdefault("_rnf_programs", {})
     key = (device.index if device.index is not None else torch.cuda.current_device(), tuple(perms))
     sig = _signature(layers)
@@ -284,6 +306,21 @@ def _program(owner, layers, perms, F, device) -> engine.Program:
     prog = engine.Program(specs, F, torch.device("cuda", key[0]))
     cache[key] = (sig, prog)
     return prog
+
+
+def _wants_grad(layers, rotation, feature) -> bool:
+    if not torch.is_grad_enabled():
+        return False
+    if rotation.requires_grad or (torch.is_tensor(feature) and feature.requires_grad):
+        return True
+    return any(t.requires_grad for l in layers for t in engine.layer_tensors(l))
+
+
+_GRAD_MESSAGE = (
+    "rotationnormflow_b200 evaluates the flow in fused, non-differentiable CUDA kernels; this call runs with autograd enabled "
+    "and {what} requires grad, so the reference would build a graph here (flow/flow.py:53-92, training at agent.py:87, "
+    "eval.py:468-477).  Wrap inference in torch.no_grad() (as eval.py:539 / agent.py:102 do); returning detached outputs "
+    "silently would make backward() a no-op for the flow.")
 
 
 def _check_rotation(rotation):
@@ -301,31 +338,50 @@ def _run(layers, perms, F, owner, rotation, feature, inverse, feature_index=None
     prog = _program(owner, layers, perms, F, R.device)
     mode = mode or engine.default_mlp_mode()
     N = R.shape[0]
-    if prog.cond_floats == 0:
-        return prog.run(R, None, 0, None, 1, inverse, mode)
-    if feature is None:
+    conditional = prog.cond_floats != 0
+    if conditional and feature is None:
         raise AssertionError("The input feature is needed in this module")
+    if conditional and feature_index is None and feature.shape[0] != N:
+        raise ValueError(f"feature has {feature.shape[0]} rows for {N} rotations (the reference asserts equality, agent.py:211,259)")
+    if _wants_grad(layers, rotation, feature if conditional else None):
+        what = "the rotation" if rotation.requires_grad else ("the feature" if (conditional and feature.requires_grad) else "a flow parameter")
+        raise NotImplementedError(_GRAD_MESSAGE.format(what=what))
+    if not conditional:
+        return prog.run(R, None, 0, None, 1, inverse, mode)
     feature = feature.to(R.device)
     if feature_index is not None:
         idx = feature_index.to(R.device, torch.int32).contiguous()
         if idx.shape[0] != N:
             raise ValueError("feature_index must have one entry per rotation")
         return prog.run(R, prog.condition(feature), feature.shape[0], idx, 0, inverse, mode)
-    if feature.shape[0] != N:
-        raise ValueError(f"feature has {feature.shape[0]} rows for {N} rotations (the reference asserts equality, agent.py:211,259)")
-    # bound the per-image constant buffer when every row carries its own feature
-    max_rows = max(1, (1 << 28) // max(1, prog.cond_floats))
-    if N <= max_rows:
-        uniq, idx, rpi = engine.dedup_rows(feature)
-        return prog.run(R, prog.condition(uniq), uniq.shape[0], idx, rpi, inverse, mode)
-    outs = []
-    for s in range(0, N, max_rows):
-        uniq, idx, rpi = engine.dedup_rows(feature[s:s + max_rows])
-        outs.append(prog.run(R[s:s + max_rows], prog.condition(uniq), uniq.shape[0], idx, rpi, inverse, mode))
-    return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+    if N == 0:
+        return prog.run(R, None, 0, None, 1, inverse, mode)
+    # ---- the reference's convention: one feature row per rotation (built by .repeat, agent.py:240-244 / eval.py:450) ----
+    if feature.stride(0) == 0 or N == 1:                         # an expanded view: one image, nothing to read
+        return prog.run(R, prog.condition(feature[:1]), 1, None, N, inverse, mode)
+    feat = feature.to(torch.float32).contiguous()
+    capturing = torch.cuda.is_current_stream_capturing()
+    cap = min(N, engine.DEDUP_CAP)
+    idx, first, count = engine.dedup_rows(feat, cap)             # device side, asynchronous
+    if N > cap and not capturing:
+        # more rows than the optimistic capacity: the run count decides (one 4-byte read; the reference itself synchronises
+        # 15 times per Mobius layer in this direction of use).  Under stream capture the capacity is a documented
+        # precondition, enforced by rnf_poison_if_overflow below.
+        B = int(count.item())
+        if B > cap:
+            max_rows = max(1, (1 << 28) // max(1, prog.cond_floats))    # bound the per-image constant buffer
+            if B > max_rows:
+                outs = [_run(layers, perms, F, owner, R[s:s + max_rows], feat[s:s + max_rows], inverse, None, mode) for s in range(0, N, max_rows)]
+                return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+            cap = B
+            idx, first, count = engine.dedup_rows(feat, cap)
+    out = prog.run(R, prog.condition_runs(feat, first, count, cap), cap, idx, 0, inverse, mode)
+    if N > cap and capturing:
+        prog.poison_if_overflow(count, cap, out[1])
+    return out
 
 
-class Flow(nn.Module):
+class Flow(_NoProgramState, nn.Module):
     """flow/flow.py:18-92."""
 
     def __init__(self, config):
@@ -387,6 +443,8 @@ class Flow(nn.Module):
         logp [B,G] if requested)."""
         from .fisher import fisher_constants
         G_ = _check_rotation(grid)
+        if torch.is_grad_enabled() and torch.is_tensor(feature) and feature.requires_grad:
+            raise NotImplementedError(_GRAD_MESSAGE.format(what="the feature"))
         prog = _program(self, list(self.layers), self._perm_rows(), self.feature_dim, G_.device)
         cond, B = None, 1
         if prog.cond_floats:

@@ -86,3 +86,24 @@ def golden(tag):
     if tag not in _cache:
         _cache[tag] = Golden(tag)
     return _cache[tag]
+
+
+# ---- per-case error table of the run (copied to profiles/ as the evidence behind the parity claims) ----------------------
+ERRORS: list = []
+
+
+def record_error(**row):
+    ERRORS.append(row)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not ERRORS:
+        return
+    path = os.environ.get("RNF_ERROR_TABLE")
+    if path is None:
+        d = os.path.join(ROOT, "gpurun_out")
+        if not os.path.isdir(d):
+            return
+        path = os.path.join(d, "error_table.json")
+    with open(path, "w") as f:
+        json.dump(ERRORS, f, indent=1)

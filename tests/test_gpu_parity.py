@@ -3,8 +3,8 @@ real reference and against the CPU oracle.  Run on the B200 box:  python -m pyte
 
 Tolerances (BASELINE.json north_star): rotations within 1e-5 max-abs, log-probs within 1e-4 relative
 (|d| / max(|ref|, 1): ldj crosses zero), grid indices / arg-max bit-exact (ties: see test_grid_*).
-For the F=2080 ModelNet configuration the reference's own fp32-vs-fp64 gap is 4.5e-5 / 6.2e-5,
-so that case is held to 1e-4 max-abs against the fp64 reference output instead.
+Where the reference's own fp32 run is further than that from its fp64 run (F=2080 ModelNet: 4.5e-5 / 6.2e-5, SURVEY.md 7.2
+item 1) the bound is the reference's own fp32-vs-fp64 error, read from the golden file (_tolerances).
 """
 import math
 import os
@@ -13,13 +13,20 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import FULL_CASES, GOLDEN, SMALL_CASES, golden, seeded_product_flow
+from conftest import FULL_CASES, GOLDEN, SMALL_CASES, golden, record_error, seeded_product_flow
 from oracle import rnf_oracle as orc
 import rotationnormflow_b200 as rnf
 from rotationnormflow_b200 import grid as rgrid
 from rotationnormflow_b200.fisher import fisher_constants
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _golden_svd_convention(monkeypatch):
+    """The golden vectors of the 4-D rotation layers (16Rot / 16UnRot) were minted by the reference on the CPU: LAPACK's sign
+    convention defines their U^T V (engine.Program._polar_factor).  test_rotation_layers_svd_backend covers the default."""
+    monkeypatch.setenv("RNF_SVD_BACKEND", "cpu")
 
 MODES = [m for m in os.environ.get("RNF_TEST_MODES", "fp32,tc,tc_row").split(",") if m]
 
@@ -43,8 +50,16 @@ def rel(a, ref):
     return ((a - ref).abs() / ref.abs().clamp(min=1.0)).max().item()
 
 
-R_TOL = {"modelnet": 1e-4}
-LDJ_TOL = {"modelnet": 2e-4}
+# BASELINE.json north_star: rotations within 1e-5 max-abs, log-probs within 1e-4 relative.  Where the REFERENCE's own fp32 run is
+# further than that from its fp64 run (the F=2080 ModelNet stack: 4.5e-5 / 6.2e-5) no fp32 implementation can
+# be held to the fixed number; the principled bound is then "no further from the fp64 reference than the reference's own fp32 run"
+# (both outputs are in the golden file), see _tolerances().
+
+
+def _tolerances(g, direction="fwd"):
+    own_R = (g.out(direction, "R", "f32").double() - g.out(direction, "R", "f64").double()).abs().max().item()
+    own_l = rel(g.out(direction, "ldj", "f32").double(), g.out(direction, "ldj", "f64").double())
+    return max(1e-5, own_R), max(1e-4, own_l), own_R, own_l
 # 4-D rotation layers use U^T V of torch.svd(I + 1e-3 noise): nearly degenerate singular values make that matrix
 # precision dependent (the reference's own fp32 and fp64 runs differ by 7e-3), so those cases are held to the fp32 run.
 TRUTH = {"s_rot": "f32", "s_rotc": "f32", "s_unrot": "f32"}
@@ -66,8 +81,11 @@ def test_forward_parity(tag, mode):
     dl64 = rel(ldj, g.out("fwd", "ldj", truth).double())
     dR32 = (R - g.out("fwd", "R", "f32").double()).abs().max().item()
     print(f"\n[{tag}/{mode}] fwd  max|dR| vs ref-fp64 {dR64:.2e}  vs ref-fp32 {dR32:.2e}   rel dldj vs ref-fp64 {dl64:.2e}")
-    assert dR64 <= R_TOL.get(tag, 1e-5)
-    assert dl64 <= LDJ_TOL.get(tag, 1e-4)
+    tol_R, tol_l, own_R, own_l = _tolerances(g) if truth == "f64" else (1e-5, 1e-4, 0.0, 0.0)
+    record_error(test="forward", case=tag, mode=mode, truth=truth, max_abs_dR=dR64, max_abs_dR_vs_ref_fp32=dR32, rel_dldj=dl64,
+                 ref_fp32_vs_fp64_dR=own_R, ref_fp32_vs_fp64_dldj=own_l, tol_dR=tol_R, tol_dldj=tol_l)
+    assert dR64 <= tol_R
+    assert dl64 <= tol_l
     # outputs stay rotations
     assert (R @ R.transpose(1, 2) - torch.eye(3, dtype=torch.float64)).abs().max() < 5e-6
     # the same call with features given once per image + a row index
@@ -99,6 +117,9 @@ def test_inverse_parity(tag, mode):
     frac_own = (own <= 1e-5).float().mean().item()
     print(f"\n[{tag}/{mode}] inv  rows within 1e-5: vs ref-fp32 {frac32:.3f}  vs ref-fp64 {frac64:.3f}  (ref fp32 vs ref fp64: {frac_own:.3f})"
           f"  worst {d64.max().item():.2e}")
+    record_error(test="inverse", case=tag, mode=mode, rows_within_1e5_vs_ref_fp64=frac64, rows_within_1e5_vs_ref_fp32=frac32,
+                 ref_fp32_rows_within_1e5_of_ref_fp64=frac_own, worst_row=d64.max().item(),
+                 round_trip_max=(Rf.cpu().double() - g.R.double()).abs().max().item())
     # Bisection returns a dyadic angle of resolution pi/2^15; one-ulp noise at a probe flips a branch and moves the
     # row by up to 1.9e-4 per Mobius layer.  Bound: as many exact rows as the reference's own
     # fp32 run (minus slack), and no row further than the flip bound.
@@ -507,3 +528,136 @@ def test_full_size_properties():
     Ro, lo = o.forward(R[sel].cpu())
     assert (Rz[sel].cpu().double() - Ro).abs().max() < 1e-5
     assert rel(ldj[sel].cpu().double(), lo) < 1e-4
+
+
+def test_dedup_rows_on_device():
+    """rnf_dedup_rows: run structure of a row-aligned feature tensor, on the device (consecutive runs only: A B A is three)."""
+    from rotationnormflow_b200 import engine
+    f = (torch.arange(12.0).reshape(3, 4) + 0.5).cuda()
+    for F in (4, 5, 2048):                                              # float4 path, scalar path, several column chunks
+        base = torch.randn(3, F, generator=torch.Generator().manual_seed(F)).cuda()
+        rows = base[[0, 0, 0, 1, 1, 2]].contiguous()
+        idx, first, count = engine.dedup_rows(rows, 6)
+        assert idx.tolist() == [0, 0, 0, 1, 1, 2] and int(count) == 3 and first[:3].tolist() == [0, 3, 5]
+        idx, first, count = engine.dedup_rows(base[[0, 1, 0]].contiguous(), 3)
+        assert idx.tolist() == [0, 1, 2] and int(count) == 3
+        idx, first, count = engine.dedup_rows(base[:1].repeat(7, 1), 7)
+        assert idx.tolist() == [0] * 7 and int(count) == 1 and int(first[0]) == 0
+        one = base[[0, 0, 1]].contiguous()
+        one[2, F - 1] = one[1, F - 1]                                     # rows differing in a single element elsewhere
+        one[2, 0] += 1.0
+        assert engine.dedup_rows(one, 3)[0].tolist() == [0, 0, 1]
+    # many rows, many runs of uneven length, capacity smaller than the run count: idx is clamped, count tells
+    g = torch.Generator().manual_seed(3)
+    lens = torch.randint(1, 400, (300,), generator=g)
+    img = torch.repeat_interleave(torch.arange(300), lens)
+    feats = torch.randn(300, 64, generator=g)
+    rows = feats[img].cuda()
+    idx, first, count = engine.dedup_rows(rows, 300)
+    assert torch.equal(idx.cpu().long(), img) and int(count) == 300
+    assert torch.equal(first.cpu().long(), torch.cumsum(lens, 0) - lens)
+    idx, first, count = engine.dedup_rows(rows, 100)
+    assert int(count) == 300 and int(idx.max()) == 99
+
+
+def test_drop_in_call_with_repeated_features():
+    """flow(rotation[N,3,3], feature.repeat(...)[N,F]) -- the literal calls of eval.py:450-453 / agent.py:240-261 -- equals the
+    feature_index form, without a host synchronisation for N <= the optimistic capacity, is CUDA-graph capturable, and reads the
+    run count back only when N exceeds it."""
+    from rotationnormflow_b200 import engine
+    g = golden("s_symsol")
+    m = _product(g)
+    F = g.feat.shape[1]
+    feat = g.feat.cuda()
+    B = feat.shape[0]
+    gen = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for N in (B * 50, engine.DEDUP_CAP + 1000):                      # below / above the capacity
+            R = orc.random_rotations(N, gen).cuda()
+            per = (N + B - 1) // B
+            idx = (torch.arange(N, device="cuda") // per).to(torch.int32)
+            rows = feat[idx.long()]                                        # materialised, as .repeat does
+            want = m(R, feat, feature_index=idx)
+            got = m(R, rows)
+            assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+            gi = m.inverse(R, rows)
+            wi = m.inverse(R, feat, feature_index=idx)
+            assert torch.equal(gi[0], wi[0]) and torch.equal(gi[1], wi[1])
+            one = m(R, feat[:1].repeat(N, 1))                              # eval.py:450: one image repeated
+            ref = m(R, feat[:1].expand(N, F))
+            assert torch.equal(one[0], ref[0]) and torch.equal(one[1], ref[1])
+        # capture: no host synchronisation anywhere on the path
+        N = 3000
+        R = orc.random_rotations(N, gen).cuda()
+        rows = feat[(torch.arange(N, device="cuda") // 1000).long()].clone()
+        eager = m(R, rows)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            m(R, rows)
+        torch.cuda.current_stream().wait_stream(side)
+        with torch.cuda.graph(graph):
+            out = m(R, rows)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out[0], eager[0]) and torch.equal(out[1], eager[1])
+        rows.copy_(feat[(torch.arange(N, device="cuda") // 1500).long()])   # different run structure, same graph
+        graph.replay()
+        torch.cuda.synchronize()
+        fresh = m(R, rows)
+        assert torch.equal(out[0], fresh[0]) and torch.equal(out[1], fresh[1])
+
+
+def test_autograd_is_refused_loudly_and_cache_hygiene():
+    """no silently detached outputs in grad mode; the packed-program cache neither blocks deepcopy / pickle nor
+    survives invalidate_cache()."""
+    import copy
+    import pickle
+    g = golden("s_symsol")
+    m = _product(g)
+    R, rows = g.R.cuda(), g.rows.cuda()
+    with pytest.raises(NotImplementedError, match="no_grad"):
+        m(R, rows)                                                         # parameters require grad, autograd is on
+    with torch.no_grad():
+        a = m(R, rows)
+    fr = rows.clone().requires_grad_(True)
+    with pytest.raises(NotImplementedError, match="feature"):
+        m(R, fr)
+    with pytest.raises(NotImplementedError):
+        m.grid_log_prob(rgrid.healpix_grid(0), g.feat.cuda().requires_grad_(True))
+    m2 = copy.deepcopy(m)                                                  # after the first call: the cache holds a ctypes handle
+    m3 = pickle.loads(pickle.dumps(m))
+    with torch.no_grad():
+        assert torch.equal(m2(R, rows)[1], a[1]) and torch.equal(m3(R, rows)[1], a[1])
+        # a write through .data does not bump the version counter: invalidate_cache() is the documented remedy
+        m.layers[1].conditioner.fc_last.bias.data.add_(0.25)
+        assert torch.equal(m(R, rows)[1], a[1])
+        m.invalidate_cache()
+        assert (m(R, rows)[1] - a[1]).abs().max() > 1e-4
+
+
+def test_rotation_layers_svd_backend(monkeypatch):
+    """16Rot / 16UnRot: U^T V is defined up to the sign convention of the SVD routine (D U^T V D).  Default backend = torch.svd on
+    the CUDA tensor (what the reference calls on a GPU); RNF_SVD_BACKEND=cpu = LAPACK, the convention of the CPU-minted goldens."""
+    from rotationnormflow_b200 import engine
+    g = golden("s_rotc")
+    m = _product(g)
+    prog_of = lambda: __import__("rotationnormflow_b200.flow", fromlist=["_program"])._program(m, list(m.layers), m._perm_rows(), m.feature_dim, torch.device("cuda", 0))
+    mats = {}
+    for backend in ("cpu", "device"):
+        monkeypatch.setenv("RNF_SVD_BACKEND", backend)
+        prog = prog_of()
+        cond = prog.condition(g.feat.cuda())
+        base = prog.n_mob * 64
+        mats[backend] = cond[:, base: base + prog.n_aff * 40].reshape(-1, prog.n_aff, 40)[:, :, :16].reshape(-1, 4, 4).cpu().double()
+    for W in mats.values():                                                # 4-D rotations either way
+        assert (W @ W.transpose(1, 2) - torch.eye(4, dtype=torch.float64)).abs().max() < 1e-5
+    # the two conventions differ by a diagonal sign matrix on both sides at most: |entries| agree
+    assert (mats["cpu"].abs() - mats["device"].abs()).abs().max() < 1e-4
+    monkeypatch.setenv("RNF_SVD_BACKEND", "device")
+    with torch.no_grad():
+        R, ldj = m(g.R.cuda(), g.rows.cuda())
+        Ri, li = m.inverse(R, g.rows.cuda())
+    assert (Ri.cpu() - g.R).abs().max() < 2e-3 and (li + ldj).abs().max() < 2e-3

@@ -211,20 +211,6 @@ def test_cpu_tensors_fail_loudly():
         m(torch.zeros(3, 3))
 
 
-def test_dedup_rows():
-    f = torch.arange(12.0).reshape(3, 4)
-    rows = f[[0, 0, 0, 1, 1, 2]]
-    uniq, idx, rpi = engine.dedup_rows(rows)
-    assert torch.equal(uniq, f) and idx.tolist() == [0, 0, 0, 1, 1, 2] and rpi == 0
-    uniq, idx, rpi = engine.dedup_rows(f[:1].expand(5, 4))
-    assert uniq.shape == (1, 4) and idx is None and rpi == 5
-    uniq, idx, rpi = engine.dedup_rows(f[:1].repeat(7, 1))
-    assert uniq.shape == (1, 4) and idx is None and rpi == 7
-    # A B A is three images, not two (consecutive runs only)
-    uniq, idx, _ = engine.dedup_rows(f[[0, 1, 0]])
-    assert uniq.shape[0] == 3 and idx.tolist() == [0, 1, 2]
-
-
 def test_shard_ranges_cover_the_grid():
     for G in (0, 1, 7, 72, 2_359_296):
         for W in (1, 2, 3, 8):
