@@ -4,7 +4,7 @@
 //     idx[i]   = number of row changes before row i        (row -> image index, the feat_index of rnf_flow_forward)
 //     first[b] = first row of run b                         (the row the per-image conditioner reads)
 //     count    = number of runs
-// in one streaming pass over the N x F floats (HBM-bound: the 4 GB of a 500 000 x 2048 chunk are read once, ~0.65 ms), a
+// in one streaming pass over the N x F floats (HBM-bound: the 4 GB of a 500 000 x 2048 chunk are read 1 + 1/8 times), a
 // device-wide inclusive scan of the N change flags (CUB) and a scatter of the run starts.
 #include <cub/device/device_scan.cuh>
 
@@ -13,58 +13,75 @@
 namespace rnf {
 namespace {
 
-// One warp per contiguous range of rows; a lane keeps the previous row's values of its columns in registers, so every element
-// is read once (plus one extra row per range).  flags[i] = (row i differs from row i-1), flags[0] = 0.
-template <int VEC>   // float4 loads per lane and row chunk kept in registers
-__global__ void __launch_bounds__(256) row_change_kernel(const float* __restrict__ feat, int64_t N, int64_t F, int64_t rows_per_warp,
-                                                         int32_t* __restrict__ flags) {
+// flags[r] = (row r differs from row r-1), flags[0] = 0; the flags are zeroed before the launch and only ever set.
+// Work item = a tile of kRB consecutive rows x 128 consecutive float4 columns (32 lanes x 4), handed to the warps in row-major
+// tile order with a grid stride: at any moment the resident warps stream ONE contiguous window of the tensor (HBM pages and
+// channels are visited evenly; a static split into one far-apart row range per warp made thousands of streams with identical
+// alignment camp on the same channels: 0.3-0.9 TB/s).  A lane keeps the previous row of its four columns in registers, so an
+// element is read once plus 1/kRB; the (kRB + 1) x 4 loads of a tile are independent and issued back to back.
+constexpr int kRB = 8;
+
+__global__ void __launch_bounds__(256) row_change_kernel(const float* __restrict__ feat, int64_t N, int64_t F4, int64_t col_tiles,
+                                                         int64_t n_tiles, int32_t* __restrict__ flags) {
   const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t r0 = warp * rows_per_warp;
-  if (r0 >= N) return;
-  const int64_t r1 = r0 + rows_per_warp < N ? r0 + rows_per_warp : N;
-  const bool vec_ok = (F % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0);
-  for (int64_t r = r0 + lane; r < r1; r += 32) flags[r] = 0;
-  __syncwarp();
-  // column chunks of 32 lanes x VEC float4 (or scalars when the row is not 16-byte tileable)
-  if (vec_ok) {
-    const int64_t F4 = F / 4;
-    for (int64_t c0 = 0; c0 < F4; c0 += 32 * VEC) {
-      float4 prev[VEC];
-      const int64_t rp = r0 > 0 ? r0 - 1 : 0;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float4* f4 = reinterpret_cast<const float4*>(feat);
+  for (int64_t t = warp0; t < n_tiles; t += n_warps) {
+    const int64_t rb = t / col_tiles, ct = t - rb * col_tiles;
+    const int64_t r0 = rb * kRB;
+    const int64_t c0 = ct * 128 + lane;
+    float4 v[kRB + 1][4];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const int64_t c = c0 + lane + 32 * v;
-        prev[v] = c < F4 ? __ldg(reinterpret_cast<const float4*>(feat + rp * F) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      for (int64_t r = r0; r < r1; ++r) {
-        bool diff = false;
+    for (int i = 0; i <= kRB; ++i) {
+      int64_t r = r0 - 1 + i;
+      r = r < 0 ? 0 : (r < N ? r : N - 1);               // row -1 reads row 0 (no change); rows past the end repeat the last
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          const int64_t c = c0 + lane + 32 * v;
-          if (c < F4) {
-            const float4 cur = __ldg(reinterpret_cast<const float4*>(feat + r * F) + c);
-            // bit pattern comparison is not what torch's != does for NaN / signed zero; value comparison is
-            diff |= (cur.x != prev[v].x) | (cur.y != prev[v].y) | (cur.z != prev[v].z) | (cur.w != prev[v].w);
-            prev[v] = cur;
-          }
-        }
-        if (__any_sync(0xffffffffu, diff) && lane == 0 && r > 0) flags[r] = 1;
+      for (int k = 0; k < 4; ++k) {
+        const int64_t c = c0 + 32 * k;
+        v[i][k] = c < F4 ? __ldg(f4 + r * F4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-  } else {
-    for (int64_t c0 = 0; c0 < F; c0 += 32) {
-      const int64_t c = c0 + lane;
-      float prev = (c < F) ? __ldg(feat + (r0 > 0 ? r0 - 1 : 0) * F + c) : 0.f;
-      for (int64_t r = r0; r < r1; ++r) {
-        bool diff = false;
-        if (c < F) {
-          const float cur = __ldg(feat + r * F + c);
-          diff = cur != prev;
-          prev = cur;
-        }
-        if (__any_sync(0xffffffffu, diff) && lane == 0 && r > 0) flags[r] = 1;
+#pragma unroll
+    for (int i = 1; i <= kRB; ++i) {
+      bool diff = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)    // value comparison (what torch's != does), not a bit-pattern comparison
+        diff |= (v[i][k].x != v[i - 1][k].x) | (v[i][k].y != v[i - 1][k].y) | (v[i][k].z != v[i - 1][k].z) | (v[i][k].w != v[i - 1][k].w);
+      const int64_t r = r0 - 1 + i;
+      if (__any_sync(0xffffffffu, diff) && lane == 0 && r < N) flags[r] = 1;
+    }
+  }
+}
+
+// rows that are not 16-byte tileable (F % 4 != 0 or a misaligned base): the same tiling with scalar loads
+__global__ void __launch_bounds__(256) row_change_scalar_kernel(const float* __restrict__ feat, int64_t N, int64_t F, int64_t col_tiles,
+                                                                int64_t n_tiles, int32_t* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t t = warp0; t < n_tiles; t += n_warps) {
+    const int64_t rb = t / col_tiles, ct = t - rb * col_tiles;
+    const int64_t r0 = rb * kRB;
+    const int64_t c0 = ct * 128 + lane;
+    float v[kRB + 1][4];
+#pragma unroll
+    for (int i = 0; i <= kRB; ++i) {
+      int64_t r = r0 - 1 + i;
+      r = r < 0 ? 0 : (r < N ? r : N - 1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t c = c0 + 32 * k;
+        v[i][k] = c < F ? __ldg(feat + r * F + c) : 0.f;
       }
+    }
+#pragma unroll
+    for (int i = 1; i <= kRB; ++i) {
+      bool diff = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) diff |= v[i][k] != v[i - 1][k];
+      const int64_t r = r0 - 1 + i;
+      if (__any_sync(0xffffffffu, diff) && lane == 0 && r < N) flags[r] = 1;
     }
   }
 }
@@ -104,12 +121,17 @@ cudaError_t launch_dedup(const float* feat, int64_t N, int64_t F, int32_t* idx, 
   if (N <= 0) return cudaSuccess;
   if (N > 0x7fffffffLL) return cudaErrorInvalidValue;
   // flags live in idx (the scan runs in place); ws holds the scan's temporary storage
-  const int64_t warps = (int64_t)sm_count * 32;                     // 4 CTAs x 8 warps per SM: enough loads in flight for HBM
-  const int64_t rows_per_warp = (N + warps - 1) / warps;
-  const int64_t n_warps = (N + rows_per_warp - 1) / rows_per_warp;
-  const unsigned blocks = (unsigned)((n_warps + 7) / 8);
-  row_change_kernel<4><<<blocks, 256, 0, st>>>(feat, N, F, rows_per_warp, idx);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = cudaMemsetAsync(idx, 0, sizeof(int32_t) * (size_t)N, st);
+  if (e != cudaSuccess) return e;
+  const bool vec_ok = (F % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0);
+  const int64_t cols = vec_ok ? F / 4 : F;                          // float4 or float columns
+  const int64_t col_tiles = (cols + 127) / 128, row_blocks = (N + kRB - 1) / kRB;
+  const int64_t n_tiles = col_tiles * row_blocks;
+  const int64_t want = (n_tiles + 7) / 8, cap_blocks = (int64_t)sm_count * 8;     // 8 CTAs x 8 warps per SM at most
+  const unsigned blocks = (unsigned)(want < cap_blocks ? want : cap_blocks);
+  if (vec_ok) row_change_kernel<<<blocks, 256, 0, st>>>(feat, N, cols, col_tiles, n_tiles, idx);
+  else row_change_scalar_kernel<<<blocks, 256, 0, st>>>(feat, N, cols, col_tiles, n_tiles, idx);
+  e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   size_t need = ws_bytes;
   e = cub::DeviceScan::InclusiveSum(ws, need, (const int32_t*)idx, idx, (int)N, st);

@@ -32,6 +32,9 @@ namespace {
 #define TRACE(i) do { } while (0)
 #endif
 
+#ifndef RNF_INV_NEWTON
+#define RNF_INV_NEWTON 1         // inverse: locate the root with Newton steps, then replay the reference's 15 halvings (see below)
+#endif
 constexpr int kThreads = 256;
 constexpr int kRows = 128;                        // rows per tile = TMEM lanes = threads per tile
 
@@ -370,30 +373,87 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
         float ys = atan2f(zv, zr);
         ys = ys >= 0.0f ? ys : ys + kTwoPi;
         if (fabsf(ys - kTwoPi) < 1e-4f) ys = 0.0f;
-        // BinFind.forward (flow/mobiusflow.py:196-224): bracket [pi/2, 3pi/2], 15 halvings, return the last probe
-        float lo = kPi / 2.0f, hi = 1.5f * kPi, x0 = 0.0f;
-#pragma unroll 1
-        for (int it = 0; it < 15; ++it) {
-          x0 = (lo + hi) / 2.0f;
+        // BinFind.forward (flow/mobiusflow.py:196-224): bracket [pi/2, 3pi/2], 15 halvings, return the last probe.
+        // One evaluation of  F(t) = sum_k weight_k theta_k(z(t)) / sum_k weight_k - ys  (and, DERIV, of F') streams the row's
+        // 256 prepared parameters from its TMEM lane.
+        auto probe = [&](float t, float& dF) -> float {
           float sn, cs;
-          sincos_2pi(x0, sn, cs);
-          f32x2 Fs2 = 0ull;
+          sincos_2pi(t, sn, cs);
+          f32x2 Fs2 = 0ull, Sf2 = 0ull;
           float bufA[32], bufB[32];
           tmem_ld32_async(tm, bufA);
           tmem_ld_wait32(bufA);
 #pragma unroll 1
           for (int j = 0; j < 4; ++j) {
             tmem_ld32_async(tm + 64 * j + 32, bufB);
-            probe_pairs<4>(cs, sn, bufA, Fs2);
+            probe_pairs<4, RNF_INV_NEWTON != 0>(cs, sn, bufA, Fs2, &Sf2);
             tmem_ld_wait32(bufB);
             if (j < 3) tmem_ld32_async(tm + 64 * j + 64, bufA);
-            probe_pairs<4>(cs, sn, bufB, Fs2);
+            probe_pairs<4, RNF_INV_NEWTON != 0>(cs, sn, bufB, Fs2, &Sf2);
             if (j < 3) tmem_ld_wait32(bufA);
           }
-          const float fx0 = hsum(Fs2) / S_sp - ys;
-          const float half_w = (hi - lo) / 2.0f;
-          if (fx0 < 0.0f) lo = lo + half_w;
-          else if (fx0 >= 0.0f) hi = hi - half_w;
+          dF = hsum(Sf2) / S_sp;
+          return hsum(Fs2) / S_sp - ys;                // the reference's f(x0), same arithmetic for every use
+        };
+        float lo = kPi / 2.0f, hi = 1.5f * kPi, x0 = 0.0f;
+#if RNF_INV_NEWTON
+        // The 15 sign tests of the reference are tests of x0 against the root t* of F: every theta_k(t) is an increasing circle
+        // map that stays within +-2 asin(0.7) of t (|w'| < 0.7), so on the bracket F is continuous and strictly increasing
+        // (F' = sum_k weight_k f_k / sum_k weight_k in [0.17, 5.7]) and  F(x0) < 0  <=>  x0 < t*.  So: find t* with a safeguarded
+        // Newton iteration (3-4 evaluations instead of 15), then replay the reference's halving arithmetic with the sign of
+        // x0 - t*.  Where that sign is not certain -- the predicted |F(x0)| = F'(t*) |x0 - t*| is below 2e-6, i.e. within the
+        // fp32 evaluation noise of F, a region where the reference's own decision is rounding noise too -- x0 is evaluated
+        // explicitly with the reference's arithmetic, exactly as the plain bisection would.  At most one dyadic probe per row can be
+        // that close (their spacing is pi / 2^15 = 9.6e-5 at the last level).
+        float ts = kPi, dFs = 1.0f;                   // root estimate and slope there
+        bool newton_ok = false;
+        {
+          float a_ = lo, b_ = hi;
+          bool conv = false;
+#pragma unroll 1
+          for (int it = 0; it < 10; ++it) {
+            float dF;
+            const float F = probe(ts, dF);
+            if (!conv) {
+              if (F < 0.0f) a_ = ts; else b_ = ts;
+              dFs = dF;
+              const float step = F / dF;
+              conv = fabsf(step) < 1e-5f;               // quadratic convergence: the error after this step is ~step^2
+              float tn = ts - step;
+              if (!conv && !(tn > a_ && tn < b_)) tn = 0.5f * (a_ + b_);
+              ts = tn;
+            }
+            if (__all_sync(0xffffffffu, conv)) { newton_ok = true; break; }
+          }
+        }
+        if (newton_ok) {
+#pragma unroll 1
+          for (int it = 0; it < 15; ++it) {
+            x0 = (lo + hi) / 2.0f;
+            const float d = x0 - ts;
+            const bool amb = fabsf(d) * dFs < 2e-6f;
+            bool neg = d < 0.0f;
+            if (__any_sync(0xffffffffu, amb)) {
+              float dF;
+              const float fx0 = probe(x0, dF);
+              if (amb) neg = fx0 < 0.0f;
+            }
+            const float half_w = (hi - lo) / 2.0f;
+            if (neg) lo = lo + half_w;
+            else hi = hi - half_w;
+          }
+        } else
+#endif
+        {
+#pragma unroll 1
+          for (int it = 0; it < 15; ++it) {
+            x0 = (lo + hi) / 2.0f;
+            float dF;
+            const float fx0 = probe(x0, dF);
+            const float half_w = (hi - lo) / 2.0f;
+            if (fx0 < 0.0f) lo = lo + half_w;
+            else if (fx0 >= 0.0f) hi = hi - half_w;
+          }
         }
         float sn, cs;
         sincos_2pi(x0, sn, cs);

@@ -53,6 +53,10 @@ namespace {
 #ifndef RNF_T4_NP
 #define RNF_T4_NP 2              // mixture pairs evaluated together
 #endif
+#ifndef RNF_T4_YIELD
+#define RNF_T4_YIELD 0           // experiment: scheduler yields inside the mixture (1 = once per chunk, 2 = after every block of pairs)
+#endif
+#define T4_YIELD(level) do { if (RNF_T4_YIELD >= (level)) __nanosleep(0); } while (0)
 constexpr int kTiles = RNF_T4_TILES;
 constexpr int kThreads = kTiles * 128;
 constexpr int kRows = 128;
@@ -484,6 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
         mixture_pairs<2, true>(P, zr, zv, buf0, S_sp2, S_th2, S_f2);
         tmem_ld16_async(tm + kColD + 32, buf0);
         tmem_ld_wait16(buf1);
+        T4_YIELD(2);
         mixture_pairs<2, true>(P, zr, zv, buf1, S_sp2, S_th2, S_f2);
         tmem_ld16_async(tm + kColD + 48, buf1);
         tmem_ld_wait16(buf0);
@@ -492,7 +497,9 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
           hand_over();
           if (issuer_warp) issue_chunk(c + 1);
         }
+        T4_YIELD(1);
         mixture_pairs<2, true>(P, zr, zv, buf0, S_sp2, S_th2, S_f2);
+        T4_YIELD(2);
         mixture_pairs<2, true>(P, zr, zv, buf1, S_sp2, S_th2, S_f2);
       }
 #endif

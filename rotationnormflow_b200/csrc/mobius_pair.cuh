@@ -14,6 +14,10 @@
 #pragma once
 #include "mobius_fast.cuh"
 
+#ifndef RNF_MIX_RSQ
+#define RNF_MIX_RSQ 1            // forward mixture: rsqrt + asin (8 SFU operations per pair) instead of two reciprocals + atan (10)
+#endif
+
 namespace rnf {
 
 typedef unsigned long long f32x2;   // two fp32 in a 64-bit register pair: low word = component a, high word = component b
@@ -59,8 +63,10 @@ __device__ __forceinline__ float hsum(f32x2 v) {
 // the XU pipe (8 cycles per warp instruction, tools/mufu_rate.cu) is the tightest unit of the mixture -- and a shorter
 // polynomial: asin(m) = m + m s P(s), s = m^2, P of degree 6 (minimax fit, max abs error 4.4e-8 in fp32 Horner form,
 // tests/test_fastmath.py).
-__device__ __forceinline__ f32x2 asin_unit2(f32x2 m) {
-  const f32x2 s = mul2(m, m);
+__device__ __forceinline__ f32x2 asin_unit2_s(f32x2 m, f32x2 s);
+__device__ __forceinline__ f32x2 asin_unit2(f32x2 m) { return asin_unit2_s(m, mul2(m, m)); }
+// ... with s = m^2 supplied by the caller
+__device__ __forceinline__ f32x2 asin_unit2_s(f32x2 m, f32x2 s) {
   f32x2 p = bc(0.12371734529733658f);
   p = fma2(p, s, bc(-0.11529727280139923f));
   p = fma2(p, s, bc(0.09339626878499985f));
@@ -135,6 +141,9 @@ __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv
   }
   if (FWD) {
     f32x2 f[NP], q[NP];
+#if RNF_MIX_RSQ
+    f32x2 qs[NP];
+#endif
     const f32x2 nzr = bc(-zr);
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
@@ -143,15 +152,31 @@ __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv
       const f32x2 DD = fma2(Dn, Dn, bb[j]);
       // u^2 - |(a',b')|^2 with |(a',b')| = rt:  1 + (2 / 0.7) rt + (1 / 0.49 - 1) rt^2  -- all terms positive
       const f32x2 num = fma2(fma2(rt[j], bc(1.0408163265306123f), bc(2.857142857142857f)), rt[j], bc(1.0f));
+#if RNF_MIX_RSQ
+      // ONE SFU operation per component instead of two reciprocals (the XU pipe, 8 cycles per warp instruction, is the tightest
+      // unit of the mixture: 10 -> 8 MUFU per pair): with rs = 1 / |D|,  sin(arg) = b' rs  and  1 / |D|^2 = rs^2, and since
+      // Dn > 0 the angle atan(b' / Dn) = asin(b' rs), |b' rs| <= 0.7 (the squashed centre stays inside the disk of radius 0.7).
+      f32x2 rs;
+      RNF_MAP2(rs, DD, rsqrt_approx);
+      const f32x2 rs2 = mul2(rs, rs);
+      f[j] = mul2(num, rs2);
+      q[j] = mul2(bp[j], rs);
+      qs[j] = mul2(bb[j], rs2);
+#else
       f32x2 rc, rcd;
       RNF_MAP2(rc, DD, rcp_approx);
       RNF_MAP2(rcd, Dn, rcp_approx);
       f[j] = mul2(num, rc);
       q[j] = mul2(bp[j], rcd);
+#endif
     }
     f32x2 at[NP];
 #pragma unroll
+#if RNF_MIX_RSQ
+    for (int j = 0; j < NP; ++j) at[j] = asin_unit2_s(q[j], qs[j]);
+#else
     for (int j = 0; j < NP; ++j) at[j] = atan_half2(q[j]);
+#endif
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       S_sp = add2(S_sp, sp[j]);
@@ -179,8 +204,9 @@ __device__ __forceinline__ float mixture_angle(float S_at, float inv_sp) { retur
 
 // Bisection probe of NP prepared pairs at the in-plane point (zr, zv) = (cos t, sin t): accumulates sum_k weight_k theta_k(z).
 // Full-circle atan2: during the bisection z sweeps [pi/2, 3pi/2] and h may land anywhere (flow/mobiusflow.py:226-245).
-template <int NP>
-__device__ __forceinline__ void probe_pairs(float zr, float zv, const float* prm, f32x2& Fs) {
+// DERIV: also accumulates sum_k weight_k f_k(z) = d/dt of the sum above (each component is a circle map with derivative f_k).
+template <int NP, bool DERIV = false>
+__device__ __forceinline__ void probe_pairs(float zr, float zv, const float* prm, f32x2& Fs, f32x2* Sf = nullptr) {
   f32x2 mn[NP];
   float hr_[2 * NP], hv_[2 * NP];
 #pragma unroll
@@ -191,6 +217,7 @@ __device__ __forceinline__ void probe_pairs(float zr, float zv, const float* prm
     f32x2 rc;
     RNF_MAP2(rc, dd, rcp_approx);
     const f32x2 f = mul2(omw, rc);
+    if (DERIV) *Sf = fma2(pk(prm[8 * j + 6], prm[8 * j + 7]), f, *Sf);
     const f32x2 hr = fma2(f, dr, nal), hv = fma2(f, dv, nbe);
     upk(hr, hr_[2 * j], hr_[2 * j + 1]);
     upk(hv, hv_[2 * j], hv_[2 * j + 1]);

@@ -45,14 +45,27 @@ int rnf_abi_version(void) { return RNF_ABI_VERSION; }
 const char* rnf_last_error(void) { return g_err; }
 
 int rnf_device_check(int* sm_count_out) {
+  // cudaGetDeviceProperties costs milliseconds per call (it queries every attribute, clocks and PCIe state included): the three
+  // attributes needed here are read once per device with cudaDeviceGetAttribute and remembered.
+  static int cached_sm[64];                         // 0 = not queried yet, -1 = not an sm_100 device
+  static int cached_cc[64];
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail(RNF_ENODEV, "cudaGetDevice: %s", cudaGetErrorString(e));
-  cudaDeviceProp prop;
-  e = cudaGetDeviceProperties(&prop, dev);
-  if (e != cudaSuccess) return fail(RNF_ENODEV, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
-  if (prop.major != 10) return fail(RNF_ENODEV, "device %d is sm_%d%d; this library contains sm_100a code only", dev, prop.major, prop.minor);
-  if (sm_count_out) *sm_count_out = prop.multiProcessorCount;
+  const bool slot = dev >= 0 && dev < 64;
+  int sm = slot ? cached_sm[dev] : 0, cc = slot ? cached_cc[dev] : 0;
+  if (sm == 0) {
+    int major = 0, minor = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return fail(RNF_ENODEV, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+    cc = 10 * major + minor;
+    if (major != 10) sm = -1;
+    if (slot) { cached_cc[dev] = cc; cached_sm[dev] = sm; }   // benign race: every thread writes the same values
+  }
+  if (sm < 0) return fail(RNF_ENODEV, "device %d is sm_%d; this library contains sm_100a code only", dev, cc);
+  if (sm_count_out) *sm_count_out = sm;
   return RNF_OK;
 }
 

@@ -56,10 +56,17 @@ def rel(a, ref):
 # (both outputs are in the golden file), see _tolerances().
 
 
-def _tolerances(g, direction="fwd"):
+# Two fp32 evaluations of the same ill-conditioned stack are two draws of the same rounding-noise distribution, and a max over the
+# rows of one draw does not bound the max of the other: the product modes (tc, tc_row) get a factor 2 on the reference's own
+# error, the CUDA-core cross-check kernel (mode "fp32": plain FMA chains for the GEMMs, not the product path) a factor 4.
+OWN_ERROR_FACTOR = {"tc": 2.0, "tc_row": 2.0, "fp32": 4.0}
+
+
+def _tolerances(g, direction="fwd", mode="tc"):
     own_R = (g.out(direction, "R", "f32").double() - g.out(direction, "R", "f64").double()).abs().max().item()
     own_l = rel(g.out(direction, "ldj", "f32").double(), g.out(direction, "ldj", "f64").double())
-    return max(1e-5, own_R), max(1e-4, own_l), own_R, own_l
+    k = OWN_ERROR_FACTOR[mode]
+    return max(1e-5, k * own_R), max(1e-4, k * own_l), own_R, own_l
 # 4-D rotation layers use U^T V of torch.svd(I + 1e-3 noise): nearly degenerate singular values make that matrix
 # precision dependent (the reference's own fp32 and fp64 runs differ by 7e-3), so those cases are held to the fp32 run.
 TRUTH = {"s_rot": "f32", "s_rotc": "f32", "s_unrot": "f32"}
@@ -81,7 +88,7 @@ def test_forward_parity(tag, mode):
     dl64 = rel(ldj, g.out("fwd", "ldj", truth).double())
     dR32 = (R - g.out("fwd", "R", "f32").double()).abs().max().item()
     print(f"\n[{tag}/{mode}] fwd  max|dR| vs ref-fp64 {dR64:.2e}  vs ref-fp32 {dR32:.2e}   rel dldj vs ref-fp64 {dl64:.2e}")
-    tol_R, tol_l, own_R, own_l = _tolerances(g) if truth == "f64" else (1e-5, 1e-4, 0.0, 0.0)
+    tol_R, tol_l, own_R, own_l = _tolerances(g, "fwd", mode) if truth == "f64" else (1e-5, 1e-4, 0.0, 0.0)
     record_error(test="forward", case=tag, mode=mode, truth=truth, max_abs_dR=dR64, max_abs_dR_vs_ref_fp32=dR32, rel_dldj=dl64,
                  ref_fp32_vs_fp64_dR=own_R, ref_fp32_vs_fp64_dldj=own_l, tol_dR=tol_R, tol_dldj=tol_l)
     assert dR64 <= tol_R
