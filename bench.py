@@ -50,7 +50,16 @@ UNIT = "rotations/s"
 # ~100 per quaternion affine layer.  SFU: ~400 forward, ~2 280 inverse.
 TENSOR_FLOPS_PER_MOBIUS = 57344
 FP32_FWD_PER_MOBIUS = 384 + 5633
-FP32_INV_PER_MOBIUS = 115384 - 57344
+FP32_INV_PER_MOBIUS = 115384 - 57344             # the reference's algorithm: 15 bisection probes
+
+
+def fp32_inv_per_mobius(evals):
+    """SURVEY.md 8(d) with E evaluations of the mixture map instead of 15: first layer 384 + preparation 64*27 + E*(64*57+25) +
+    Jacobian 64*12 + 65.  The kernel locates the root with Newton steps and replays the reference's halvings (csrc/flow_row.cu), so it
+    EXECUTES fewer evaluations than the reference's 15; the roofline is quoted on the work executed, measured by a device counter."""
+    return 384 + 64 * 27 + evals * (64 * 57 + 25) + 64 * 12 + 65
+
+
 AFFINE_FLOPS = 100
 SPLIT_ISSUE_FACTOR = 3.25        # error-compensated split: 3 fp16 products + one K=16 block MMA per K=64 GEMM
 
@@ -296,9 +305,10 @@ def _n_mobius(flow):
     return sum(1 for l in flow.layers if l.kind == "mobius")
 
 
-def _roofline(pk, mode, rot_per_launch, kernel_s, n_mob, n_aff, inverse=False, kernel=None, traffic=None):
+def _roofline(pk, mode, rot_per_launch, kernel_s, n_mob, n_aff, inverse=False, kernel=None, traffic=None, evals=None):
     tensor = TENSOR_FLOPS_PER_MOBIUS * n_mob
-    fp32 = (FP32_INV_PER_MOBIUS if inverse else FP32_FWD_PER_MOBIUS) * n_mob + AFFINE_FLOPS * n_aff
+    per_mob = (fp32_inv_per_mobius(evals) if evals is not None else FP32_INV_PER_MOBIUS) if inverse else FP32_FWD_PER_MOBIUS
+    fp32 = per_mob * n_mob + AFFINE_FLOPS * n_aff
     ach = tensor * rot_per_launch / kernel_s / 1e12
     fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
     ach32 = fp32 * rot_per_launch / kernel_s / 1e12
@@ -314,6 +324,11 @@ def _roofline(pk, mode, rot_per_launch, kernel_s, n_mob, n_aff, inverse=False, k
         r["bound"] = "fp32 (CUDA cores; nominal peak 148 SMs x 128 lanes x 2 x sm_max_mhz -- MEASURED_PEAKS.json has no FP32 figure)"
         r["achieved"], r["peak"], r["frac"] = ach32, fp32_peak, ach32 / fp32_peak
         r["tensor_part"] = {"achieved": ach, "peak": pk["bf16_sustained"], "frac": ach / pk["bf16_sustained"]}
+        ref32 = FP32_INV_PER_MOBIUS * n_mob + AFFINE_FLOPS * n_aff
+        r["evaluations_per_sample_layer"] = {"executed": evals, "reference_algorithm": 15,
+                                             "note": "Newton root + replay of the reference's 15 halvings; explicit evaluation only where the sign is within fp32 noise"}
+        r["reference_algorithm_equivalent"] = {"fp32_flops_per_rotation": ref32, "achieved": ref32 * rot_per_launch / kernel_s / 1e12, "unit": "TFLOP/s",
+                                               "note": "the same samples/s expressed in the FLOPs the reference's 15-probe bisection would execute"}
     return r
 
 
@@ -514,6 +529,24 @@ def run_rows_config(ctx, mode, steps, warmup):
     return rec, (cfg, flow)
 
 
+def count_evaluations(flow, rows, feat, idx, mode):
+    """Evaluations of the mixture map per (sample, Mobius layer) the inverse kernel executes, from its device counter (untimed run)."""
+    import ctypes as C
+    from rotationnormflow_b200 import _cabi
+    lib = _cabi.load()
+    counter = torch.zeros(1, dtype=torch.int64, device=rows.device)
+    lib.rnf_debug_set_probe_counter.argtypes = [C.c_void_p]
+    lib.rnf_debug_set_probe_counter.restype = None
+    lib.rnf_debug_set_probe_counter(C.c_void_p(counter.data_ptr()))
+    try:
+        flow.inverse(rows, feat, feature_index=idx, mlp_mode=mode)
+        torch.cuda.synchronize()
+    finally:
+        lib.rnf_debug_set_probe_counter(C.c_void_p(0))
+    n = -(-rows.shape[0] // 128) * 128                              # whole tiles execute
+    return float(counter.item()) / (n * _n_mobius(flow)) if mode != "fp32" else 15.0
+
+
 def run_sampling_config(ctx, mode, steps, warmup, n_img=64, n_per=1_000_000):
     """Config 4: symsol2.yml Flow.inverse, n_per base rotations per image x n_img images; images split over the ranks."""
     from rotationnormflow_b200 import grid as rgrid
@@ -554,6 +587,7 @@ def run_sampling_config(ctx, mode, steps, warmup, n_img=64, n_per=1_000_000):
 
         t, _ = ctx.wall(e2e, max(1, min(steps, 3)), 1)
         S, ldj = step()
+        evals = count_evaluations(flow, rows[:262144], feat, idx[:262144], mode)
         chk = min(b * n_per, 200_000)
         Rf, lf = flow(S[:chk], feat, feature_index=idx[:chk], mlp_mode=mode)
     k_s = statistics.mean(a.elapsed_time(c) for a, c in timed_ev) * 1e-3
@@ -563,10 +597,10 @@ def run_sampling_config(ctx, mode, steps, warmup, n_img=64, n_per=1_000_000):
         "metric": METRIC_SAMPLING, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": ctx.world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32" if mode == "fp32" else "f32 (conditioner GEMMs: split-fp16 tensor-core operands, fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[3]: symsol2.yml (F=512, 42 layers) Flow.inverse (15-probe bisection), {n_per} base rotations per image x {n_img} images",
+        "config": {"workload": f"BASELINE configs[3]: symsol2.yml (F=512, 42 layers) Flow.inverse (BinFind root-solve), {n_per} base rotations per image x {n_img} images",
                    "samples_per_step": total, "mlp_mode": mode, "l2": "flushed between timed steps (256 MiB write)", "weights": "random init seed 0",
                    "parallelism": f"images split over {ctx.world} rank(s), no collective"},
-        "roofline": _roofline(pk, mode, b * n_per, k_s, n_mob, len(flow.layers) - n_mob, inverse=True, kernel="flow_row_kernel<inverse>"),
+        "roofline": _roofline(pk, mode, b * n_per, k_s, n_mob, len(flow.layers) - n_mob, inverse=True, kernel="flow_row_kernel<inverse>", evals=evals),
         "clocks": clk.summary(),
         "e2e": {"value": total / t, "unit": UNIT, "h2d_bytes_per_step": int(n_per * 36 + b * 512 * 4), "d2h_bytes_per_step": int(b * 36)},
         "gpu_launches": int(steps * 3),

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RNF_ABI_VERSION 8
+#define RNF_ABI_VERSION 9
 
 /* error codes */
 #define RNF_OK 0
@@ -38,6 +38,13 @@ extern "C" {
 /* layer kinds (flow/flow.py:36-51 builds a list of exactly these two families) */
 #define RNF_LAYER_MOBIUS 0 /* flow/mobiusflow.py:27-183  MobiusFlow                                   */
 #define RNF_LAYER_AFFINE 1 /* flow/squeezetrans.py:33-38 calculate_16, and flow/rottrans.py:8-66 (has_ldj=0) */
+/* ablation replacements of the affine layer (flow/affineflow.py:27-41,55-70); parameter block per direction:           */
+#define RNF_LAYER_SMITH9 2  /* calculate_9   squeezetrans.py:197-232: 3x3 M (forward) / inv(M); Gram-Schmidt + log-det   */
+#define RNF_LAYER_SMITH36 3 /* calculate_36  squeezetrans.py:291-331: 6x6 M / inv(M) on the 6-D representation           */
+#define RNF_LAYER_POLAR9L 4 /* calculate_9_l rottrans.py:69-72: polar factor of M R (inverse block: M^T); log-det 0       */
+#define RNF_LAYER_POLAR9R 5 /* calculate_9_r rottrans.py:75-78: polar factor of R M (inverse block: M^T); log-det 0       */
+#define RNF_LAYER_RIGHT9 6  /* calculate_9_r_smith rottrans.py:81-91: R Q, Q = Gram-Schmidt(M) (inverse block: Q^T)       */
+#define RNF_AFFINE_BLOCK_FLOATS 80 /* per affine-family layer: forward block [0,40), inverse-direction block [40,80)     */
 
 /* kernel selection for the conditioner MLP (flow/condition.py:24-30) */
 #define RNF_MLP_FP32 0    /* FP32 CUDA-core FMA: the exact-precision path                             */
@@ -51,7 +58,8 @@ extern "C" {
  *               (r, r+1, r+2) mod 3 of R.  Ignored by affine layers.
  *   cond_slot : >= 0 -> this layer reads per-image data produced by rnf_flow_condition():
  *                 Mobius: 64 floats  W_f.feature  (first conditioner layer hoisted per image)
- *                 affine: the 4x4 matrix of Condition16Trans / ConditionRot for that image
+ *                 affine: the parameter block (RNF_AFFINE_BLOCK_FLOATS floats) of that image: the 4x4 matrix of Condition16Trans /
+                         ConditionRot, or the 3x3 / 6x6 matrix of an ablation layer
  *               -1 -> unconditional.
  *   has_ldj   : affine only. 1 = log|det W| - 4 log|Wq| (squeezetrans.py:38); 0 = rotation layer (rottrans.py:21).
  *   w_off     : float offset of this layer's block inside the packed weight buffer (layout: DESIGN.md).
@@ -73,7 +81,9 @@ typedef struct rnf_model_desc {
   int32_t F;              /* feature width seen by the flow (0 = unconditional)                      */
   int32_t n_mobius_slots; /* conditional Mobius layers                                               */
   int32_t n_affine_slots; /* conditional affine / rot layers                                         */
-  int32_t affine_is_rot;  /* 1: conditional affine slots are ConditionRot (SVD polar factor)          */
+  int32_t affine_is_rot;  /* conditional affine slots: 0 = Condition16Trans (matrix, inverse and log-dets written by
+                             rnf_flow_condition), 1 = ConditionRot (matrix written, the caller replaces it by its SVD polar
+                             factor), 2 = ablation layers: the caller fills the slots' parameter blocks itself            */
   int64_t wf_off;         /* [n_mobius_slots + n_affine_slots][H][F] first-layer feature weights     */
   int64_t caff_off;       /* [n_affine_slots] blocks of the conditional-affine MLP tails             */
   int64_t n_floats;       /* total floats in the packed buffer                                       */
@@ -207,6 +217,30 @@ int rnf_fisher_log_prob(const float* A9_dev, const float* c_dev, int64_t B, cons
  * gt_dev [B,K,3,3] -> out_dev [B] = angle (radians) to the closest ground-truth rotation.  Post-path metric.
  */
 int rnf_min_geodesic(const float* est_dev, const float* gt_dev, int64_t B, int64_t K, float* out_dev, void* stream);
+
+/*
+ * Differentiable per-layer operators (csrc/train_ops.cu): what Flow.forward / Flow.inverse run when autograd is on -- training,
+ * agent.py:87; eval.py:468-477 -- or when config.segments != 64.  The conditioner MLP (flow/condition.py:24-30) stays a sequence of
+ * library GEMMs on the caller's side (its backward is the autograd of those); these are the Mobius mixture (flow/mobiusflow.py:58-85
+ * forward, :141-183 inverse with BinFind.forward, :196-224) and calculate_16 (flow/squeezetrans.py:33-38), forward and
+ * vector-Jacobian product, any number K <= rnf_train_max_components() of mixture components, one rotation per thread, FP32.
+ *   R_dev [N,3,3]; out_dev [N,4K] conditioner output (K logits, then K x 3 centres); perm = first column of the cyclic row.
+ *   forward : R_out_dev [N,3,3], ldj_dev [N] (the layer's own log-det, inverse direction included), theta_dev [N] (mixture angle /
+ *             returned bisection root, needed by the backward of the inverse direction)
+ *   backward: G_Rout_dev [N,3,3], g_ldj_dev [N] incoming; G_R_dev [N,3,3], G_out_dev [N,4K] outgoing.  Rotation gradients are
+ *             TANGENTIAL (R [g]x / 2): the component that reaches parameters and features; BinFind.backward's implicit-function
+ *             rule (flow/mobiusflow.py:248-273) is the inverse-direction case.
+ *   affine  : W_dev [N,4,4] per-row matrices; loglen = log|W q|; the caller adds log|det W| itself.
+ */
+int rnf_train_max_components(void);
+int rnf_train_mobius_forward(const float* R_dev, const float* out_dev, int64_t N, int K, int perm, int inverse, float* R_out_dev,
+                             float* ldj_dev, float* theta_dev, void* stream);
+int rnf_train_mobius_backward(const float* R_dev, const float* out_dev, int64_t N, int K, int perm, int inverse, const float* theta_dev,
+                              const float* R_out_dev, const float* G_Rout_dev, const float* g_ldj_dev, float* G_R_dev, float* G_out_dev,
+                              void* stream);
+int rnf_train_affine_forward(const float* R_dev, const float* W_dev, int64_t N, float* R_out_dev, float* loglen_dev, void* stream);
+int rnf_train_affine_backward(const float* R_dev, const float* W_dev, int64_t N, const float* R_out_dev, const float* G_Rout_dev,
+                              const float* g_loglen_dev, float* G_R_dev, float* G_W_dev, void* stream);
 
 #ifdef __cplusplus
 }

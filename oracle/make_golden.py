@@ -107,10 +107,7 @@ def grid_case():
     print(f"grid -> {os.path.getsize(path)/1024:.0f} KiB")
 
 
-def main():
-    os.makedirs(OUT, exist_ok=True)
-    torch.set_num_threads(os.cpu_count() or 1)
-    # small cases: weights stored in the fixture
+def small_cases():
     flow_case("s_uncond", "raw", 3, 256, 0, True, layers=3)
     flow_case("s_symsol", "symsol", 4, 256, 4, True, layers=2, feature_dim=24)
     flow_case("s_modelnet", "modelnet_fisher", 5, 256, 4, True, with_fisher=True, layers=2, feature_dim=16, embedding_dim=8)
@@ -120,12 +117,40 @@ def main():
     flow_case("s_rotc", "modelnet_uni", 9, 128, 2, True, layers=1, rot="16Rot", feature_dim=8, embedding=0)
     flow_case("s_unrot", "symsol", 10, 128, 2, True, layers=2, rot="16UnRot", feature_dim=8)
     flow_case("s_mobonly", "raw", 11, 128, 0, True, layers=2, rot="None")
-    # full-size cases (BASELINE.json configs 1-4): weights regenerated from the seed
+
+
+def ablation_cases():
+    """Ablation replacements of the affine layer (flow/affineflow.py:27-41,55-70), unconditional and conditional."""
+    flow_case("s_smith9", "raw", 12, 128, 0, True, layers=2, rot="9TransLSmith")
+    flow_case("s_smith9lu", "raw", 13, 128, 0, True, layers=2, rot="9TransLSmith", lu=1)
+    flow_case("s_smith36", "raw", 14, 128, 0, True, layers=2, rot="36Trans")
+    flow_case("s_polar9l", "raw", 15, 128, 0, True, layers=2, rot="9TransLSVD")
+    flow_case("s_polar9r", "raw", 16, 128, 0, True, layers=2, rot="9TransRSVD")
+    flow_case("s_right9", "raw", 17, 128, 0, True, layers=2, rot="9TransRSmith")
+    flow_case("s_smith9c", "modelnet_uni", 18, 128, 2, True, layers=2, rot="9TransLSmith", feature_dim=8, embedding=0)
+    flow_case("s_smith36c", "modelnet_uni", 19, 128, 2, True, layers=2, rot="36Trans", feature_dim=8, embedding=0)
+    flow_case("s_polar9lc", "modelnet_uni", 20, 128, 2, True, layers=2, rot="9TransLSVD", feature_dim=8, embedding=0)
+    flow_case("s_polar9rc", "modelnet_uni", 21, 128, 2, True, layers=2, rot="9TransRSVD", feature_dim=8, embedding=0)
+    flow_case("s_right9c", "modelnet_uni", 22, 128, 2, True, layers=2, rot="9TransRSmith", feature_dim=8, embedding=0)
+
+
+def full_cases():
+    """BASELINE.json configs 1-4: weights regenerated from the seed."""
     flow_case("raw", "raw", 0, 512, 0, False)
     flow_case("symsol2048", "symsol", 0, 512, 4, False, feature_dim=2048)
     flow_case("symsol2", "symsol2", 0, 256, 4, False)
     flow_case("modelnet", "modelnet_fisher", 0, 256, 4, False, with_fisher=True)
-    grid_case()
+
+
+GROUPS = {"small": small_cases, "ablation": ablation_cases, "full": full_cases, "grid": grid_case}
+
+
+def main():
+    """`python -m oracle.make_golden [group ...]`: all groups by default (small, ablation, full, grid)."""
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    for name in (sys.argv[1:] or list(GROUPS)):
+        GROUPS[name]()
 
 
 if __name__ == "__main__":

@@ -58,7 +58,8 @@ def feature_dim_of(cfg) -> int:
 
 
 def _affine_kind(cfg, first_layer_condition=False):
-    """Returns one of None, 'aff_u','aff_c','aff_lu','aff_clu','rot_u','rot_c' or 'unsupported:<rot>'."""
+    """Returns one of None, 'aff_u','aff_c','aff_lu','aff_clu','rot_u','rot_c', an ablation kind
+    ('smith9|smith36|polar9l|polar9r|right9' + '_u'|'_c', 'smith9_lu') or 'unsupported:<what>'."""
     rot, lu = cfg.rot, bool(cfg.lu)
     if first_layer_condition:
         if rot == "16UnTrans":
@@ -72,8 +73,14 @@ def _affine_kind(cfg, first_layer_condition=False):
         table = {"16Trans": "aff_lu" if lu else "aff_u", "16Rot": "rot_u"}
     if rot in table:
         return table[rot]
-    ablation = {"36Trans", "9TransLSVD", "9TransRSVD", "9TransLSmith", "9TransRSmith"}
-    return ("unsupported:" + rot) if rot in ablation else None
+    # ablation replacements of the affine layer (flow/affineflow.py:27-41,55-70)
+    ablation = {"36Trans": "smith36", "9TransLSVD": "polar9l", "9TransRSVD": "polar9r", "9TransRSmith": "right9",
+                "9TransLSmith": "smith9"}
+    if rot in ablation:
+        if rot == "9TransLSmith" and lu:
+            return "unsupported:Condition9TransLU" if cfg.condition else "smith9_lu"
+        return ablation[rot] + ("_c" if cfg.condition else "_u")
+    return None
 
 
 def layer_plan(cfg):
@@ -207,13 +214,43 @@ def bisect(ystar, r, v, pi, w):
     return x0
 
 
+def _theta_of(x0, r, v, pi, w):
+    """BinFind._forward_theta (flow/mobiusflow.py:230-245)."""
+    z = r * torch.cos(x0) + v * torch.sin(x0)
+    h, _ = _mobius_h(z, w)
+    return (pi * _wrapped_angles(h, r, v)).sum(1, keepdim=True)
+
+
+class BinFindWithGrad(torch.autograd.Function):
+    """BinFind (flow/mobiusflow.py:189-273) including its backward: the implicit-function gradient at the returned root."""
+
+    @staticmethod
+    def forward(ctx, y, r, v, pi, w):
+        x0 = bisect(y, r, v, pi, w)
+        ctx.save_for_backward(x0.detach(), r.detach(), v.detach(), pi.detach(), w.detach())
+        return x0
+
+    @staticmethod
+    def backward(ctx, x_grad):
+        x, r, v, pi, w = (t.clone().requires_grad_(True) for t in ctx.saved_tensors)
+        with torch.enable_grad():
+            gx, gr, gv, gpi, gw = torch.autograd.grad(_theta_of(x, r, v, pi, w), (x, r, v, pi, w), torch.ones_like(x_grad))
+        ok = gx != 0                                                         # :262-272
+        y_grad = torch.where(ok, 1 / gx, torch.zeros_like(gx)) * x_grad
+        r_grad = torch.where(ok, -gr / gx, torch.zeros_like(gr)) * x_grad
+        v_grad = torch.where(ok, -gv / gx, torch.zeros_like(gv)) * x_grad
+        w_grad = torch.where(ok.unsqueeze(-1), -gw / gx.unsqueeze(-1), torch.zeros_like(gw)) * x_grad.unsqueeze(-1)
+        pi_grad = torch.where(ok, -gpi / gx, torch.zeros_like(gpi)) * x_grad
+        return y_grad, r_grad, v_grad, pi_grad, w_grad
+
+
 def mobius_inverse(sd, prefix, R, p, feature, K, explicit_jacobian=False):
     tx, ty = R[:, :, p[0]], R[:, :, p[1]]
     r, v, pi, w = _mobius_prep(sd, prefix, tx, ty, feature, K)
     tt = torch.atan2((tx * v).sum(-1), (tx * r).sum(-1)).reshape(-1, 1)
     tt = torch.where(tt >= 0, tt, tt + 2 * math.pi)
     tt = torch.where(abs(tt - 2 * math.pi) < 1e-4, torch.zeros_like(tt), tt)   # :163-167
-    th = bisect(tt, r, v, pi, w)
+    th = BinFindWithGrad.apply(tt, r, v, pi, w) if torch.is_grad_enabled() else bisect(tt, r, v, pi, w)
     x = r * torch.cos(th) + v * torch.sin(th)
     if explicit_jacobian:
         ldj = _explicit_ldj(x, r, v, pi, w)
@@ -288,6 +325,97 @@ def affine_matrix(sd, prefix, kind, feature, inverse):
 
 
 # ----------------------------------------------------------------------------------------------
+# ablation layers                                (flow/squeezetrans.py:177-361, flow/rottrans.py:69-181)
+# ----------------------------------------------------------------------------------------------
+_GENERATORS = ((0, 1), (0, 2), (1, 2))          # G_k = e_ab - e_ba for (a, b) in this order  (squeezetrans.py:198-199)
+
+
+def _generators(dtype, device):
+    G = torch.zeros(3, 3, 3, dtype=dtype, device=device)
+    for k, (a, b) in enumerate(_GENERATORS):
+        G[k, a, b], G[k, b, a] = 1.0, -1.0
+    return G
+
+
+def _normalize_t(v, dv):
+    """accp_normalize (squeezetrans.py:177-188): v [N,3], tangents dv [3,N,3]."""
+    n = v.norm(dim=-1, keepdim=True)
+    dn = (dv * v).sum(-1, keepdim=True) / n
+    return v / n, dv / n - v * dn / n ** 2
+
+
+def _smith_tail(c0, dc0, c1, dc1):
+    """Gram-Schmidt with tangent propagation and the log-det of squeezetrans.py:209-232 (shared by calculate_9 / calculate_36)."""
+    t0, dt0 = _normalize_t(c0, dc0)
+    dot = (t0 * c1).sum(-1, keepdim=True)
+    ddot = (dt0 * c1 + t0 * dc1).sum(-1, keepdim=True)
+    t1, dt1 = _normalize_t(c1 - dot * t0, dc1 - (ddot * t0 + dot * dt0))
+    t2 = torch.linalg.cross(t0, t1, dim=-1)
+    dt2 = torch.linalg.cross(t0.expand_as(dt1), dt1, dim=-1) + torch.linalg.cross(dt0, t1.expand_as(dt0), dim=-1)
+    T = torch.stack([t0, t1, t2], dim=-1)                       # [N,3,3], columns
+    dT = torch.stack([dt0, dt1, dt2], dim=-1)                   # [3,N,3,3]
+    delta = dT @ T.transpose(-1, -2)
+    vec = torch.stack([delta[..., 0, 1], delta[..., 0, 2], delta[..., 1, 2]], dim=-1)    # [3(k),N,3]
+    return T, det3(vec.transpose(0, 1)).abs().log()
+
+
+def smith9(M, R):
+    """calculate_9 (squeezetrans.py:197-232): A = M R, tangents A G_k."""
+    A = M.reshape(-1, 3, 3) @ R
+    dA = torch.einsum("nab,kbc->knac", A, _generators(R.dtype, R.device))
+    return _smith_tail(A[..., 0], dA[..., 0], A[..., 1], dA[..., 1])
+
+
+def smith36(M, R):
+    """calculate_36 (squeezetrans.py:291-331): 6-D vector (R[:,0], R[:,1]) and its tangents under G_k R, mapped by the 6x6 M."""
+    M = M.reshape(-1, 6, 6)
+    dR = torch.einsum("kab,nbc->knac", _generators(R.dtype, R.device), R)
+    v = torch.cat([R[..., 0], R[..., 1]], dim=-1)
+    dv = torch.cat([dR[..., 0], dR[..., 1]], dim=-1)
+    t = torch.einsum("nab,nb->na", M.expand(R.shape[0], 6, 6), v)
+    dt = torch.einsum("nab,knb->kna", M.expand(R.shape[0], 6, 6), dv)
+    return _smith_tail(t[..., :3], dt[..., :3], t[..., 3:], dt[..., 3:])
+
+
+def polar9(M, R, left):
+    """calculate_9_l / calculate_9_r (rottrans.py:69-78): U V^T of svd(M R) / svd(R M); log-det 0."""
+    A = (M.reshape(-1, 3, 3) @ R) if left else (R @ M.reshape(-1, 3, 3))
+    U, _, V = torch.svd(A)
+    return U @ V.transpose(-1, -2), torch.zeros(R.shape[0], dtype=R.dtype, device=R.device)
+
+
+def right9(M, R, inverse):
+    """calculate_9_r_smith (rottrans.py:81-91)."""
+    M = M.reshape(-1, 3, 3)
+    m0 = M[..., 0] / M[..., 0].norm(dim=-1, keepdim=True)
+    m1 = M[..., 1] - (m0 * M[..., 1]).sum(dim=-1, keepdim=True) * m0
+    m1 = m1 / m1.norm(dim=-1, keepdim=True)
+    Q = torch.stack([m0, m1, torch.linalg.cross(m0, m1, dim=-1)], dim=-1)
+    if inverse:
+        Q = Q.transpose(-1, -2)
+    return R @ Q, torch.zeros(R.shape[0], dtype=R.dtype, device=R.device)
+
+
+def ablation_layer(sd, prefix, kind, R, feature, inverse):
+    """One ablation layer in the requested direction: the module classes of squeezetrans.py:235-361 / rottrans.py:94-181."""
+    base = kind.split("_")[0]
+    n = 6 if base == "smith36" else 3
+    if kind.endswith("_c"):
+        M = conditioner(sd, prefix + "net.", feature).reshape(-1, n, n) + torch.eye(n, dtype=R.dtype, device=R.device)
+    elif kind == "smith9_lu":
+        M = lu_weight(sd, prefix + "mat.")
+    else:
+        M = sd[prefix + "mat"].unsqueeze(0)
+    if base in ("smith9", "smith36"):
+        if inverse:
+            M = torch.linalg.inv(M)
+        return smith9(M, R) if base == "smith9" else smith36(M, R)
+    if base in ("polar9l", "polar9r"):
+        return polar9(M.transpose(-1, -2) if inverse else M, R, base == "polar9l")
+    return right9(M, R, inverse)
+
+
+# ----------------------------------------------------------------------------------------------
 # the composed flow                                                       (flow/flow.py:53-92)
 # ----------------------------------------------------------------------------------------------
 class OracleFlow:
@@ -309,9 +437,12 @@ class OracleFlow:
         self.explicit = explicit_jacobian
 
     def _run(self, R, feature, inverse):
-        cfg = self.cfg
         R = R.detach().to(self.device, self.dtype)
-        feature = None if (feature is None or not cfg.condition) else feature.detach().to(self.device, self.dtype)
+        feature = None if (feature is None or not self.cfg.condition) else feature.detach().to(self.device, self.dtype)
+        return self._run_graph(R, feature, inverse)
+
+    def _run_graph(self, R, feature, inverse):
+        cfg = self.cfg
         rows = permute_rows(cfg, self.plan, inverse)
         ldjs = torch.zeros(R.shape[0], dtype=self.dtype, device=self.device)
         order = range(len(self.plan) - 1, -1, -1) if inverse else range(len(self.plan))
@@ -320,6 +451,8 @@ class OracleFlow:
             if kind == "mobius":
                 fn = mobius_inverse if inverse else mobius_forward
                 R, ldj = fn(self.sd, pre, R, p, feature, self.K, self.explicit)
+            elif kind.split("_")[0] in ("smith9", "smith36", "polar9l", "polar9r", "right9"):
+                R, ldj = ablation_layer(self.sd, pre, kind, R, feature, inverse)
             else:
                 W, has_ldj = affine_matrix(self.sd, pre, kind, feature, inverse)
                 R, ldj = quat_affine(W, R, has_ldj)
@@ -329,6 +462,14 @@ class OracleFlow:
     def forward(self, R, feature=None):
         with torch.no_grad():
             return self._run(R, feature, False)
+
+    def with_grad(self, R, feature=None, inverse=False):
+        """The same evaluation with autograd on (what the reference does outside torch.no_grad(): training at agent.py:87, the
+        nll_grad evaluation at eval.py:468-477); make entries of ``self.sd`` / ``feature`` require grad before calling."""
+        with torch.enable_grad():
+            R = R.to(self.device, self.dtype)
+            feature = None if (feature is None or not self.cfg.condition) else feature.to(self.device, self.dtype)
+            return self._run_graph(R, feature, inverse)
 
     def inverse(self, R, feature=None):
         with torch.no_grad():

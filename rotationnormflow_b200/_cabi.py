@@ -11,10 +11,11 @@ import threading
 
 from . import build as _build
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 RNF_LAYER_MOBIUS = 0
 RNF_LAYER_AFFINE = 1
+RNF_LAYER_SMITH9, RNF_LAYER_SMITH36, RNF_LAYER_POLAR9L, RNF_LAYER_POLAR9R, RNF_LAYER_RIGHT9 = 2, 3, 4, 5, 6
 RNF_MLP_FP32 = 0
 RNF_MLP_TC = 1
 RNF_MLP_TC_ROW = 2
@@ -68,6 +69,11 @@ _SIGNATURES = {
     "rnf_dedup_rows": (C.c_int, [_P, _I64, _I64, _P, _P, _I64, _P, _P, _I64, _P]),
     "rnf_flow_condition_runs": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P]),
     "rnf_poison_if_overflow": (C.c_int, [_P, _I64, _P, _I64, _P]),
+    "rnf_train_max_components": (C.c_int, []),
+    "rnf_train_mobius_forward": (C.c_int, [_P, _P, _I64, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "rnf_train_mobius_backward": (C.c_int, [_P, _P, _I64, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "rnf_train_affine_forward": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
+    "rnf_train_affine_backward": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "rnf_flow_forward": (C.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _P, C.c_int, _P]),
     "rnf_flow_inverse_scratch_floats": (_I64, [_P, _I64]),
     "rnf_flow_inverse": (C.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P, C.c_int, _P]),

@@ -20,6 +20,8 @@ struct Rot9 {
 
 namespace ablation {
 
+__device__ __forceinline__ void col3(const float A[9], int c, float o[3]) { o[0] = A[c]; o[1] = A[3 + c]; o[2] = A[6 + c]; }
+
 // normalise v and propagate NT tangents (squeezetrans.py accp_normalize): t = v / |v|, dt = d/|v| - v (v.d) / |v|^3
 template <int NT>
 __device__ __forceinline__ void normalize_with_tangents(const float v[3], const float d[NT][3], float t[3], float dt[NT][3]) {
@@ -85,7 +87,7 @@ __device__ __forceinline__ float smith9(const float* __restrict__ M, float R[9])
 #pragma unroll
     for (int j = 0; j < 3; ++j) A[3 * i + j] = M[3 * i] * R[j] + M[3 * i + 1] * R[3 + j] + M[3 * i + 2] * R[6 + j];
   float a0[3], a1[3], a2[3];
-  get_col(A, 0, a0); get_col(A, 1, a1); get_col(A, 2, a2);
+  col3(A, 0, a0); col3(A, 1, a1); col3(A, 2, a2);
   float dc0[3][3], dc1[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
@@ -99,7 +101,7 @@ __device__ __forceinline__ float smith9(const float* __restrict__ M, float R[9])
 __device__ __forceinline__ float smith36(const float* __restrict__ M6, float R[9]) {
   float v[6], dv[3][6];
   float r0[3], r1[3];
-  get_col(R, 0, r0); get_col(R, 1, r1);
+  col3(R, 0, r0); col3(R, 1, r1);
 #pragma unroll
   for (int i = 0; i < 3; ++i) { v[i] = r0[i]; v[3 + i] = r1[i]; }
   // G_0 u = (u1, -u0, 0), G_1 u = (u2, 0, -u0), G_2 u = (0, u2, -u1)
@@ -164,7 +166,7 @@ __device__ __forceinline__ void matmul3(const float* __restrict__ A, const float
 }  // namespace ablation
 
 // One ablation layer on one rotation.  W: the layer's parameter block for the requested direction (rnf_abi.h layer kinds).
-__device__ __noinline__ Rot9 ablation_layer(int kind, const float* __restrict__ W, Rot9 in) {
+static __device__ __noinline__ Rot9 ablation_layer(int kind, const float* __restrict__ W, Rot9 in) {
   Rot9 out = in;
   out.ldj = 0.0f;
   float M[9];

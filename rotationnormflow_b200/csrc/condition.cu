@@ -160,7 +160,9 @@ __global__ void __launch_bounds__(64) cond_affine_kernel(const float* __restrict
 cudaError_t launch_condition(const rnf_flow* f, const float* feat, int64_t B, float* cond, cudaStream_t st,
                              const int32_t* row_index, const int32_t* count) {
   const rnf_model_desc& m = f->model;
-  const int S = m.n_mobius_slots + m.n_affine_slots;
+  // affine_is_rot == 2: the conditional affine slots belong to ablation layers whose blocks the caller fills (rnf_abi.h)
+  const int n_aff_dev = m.affine_is_rot == 2 ? 0 : m.n_affine_slots;
+  const int S = m.n_mobius_slots + n_aff_dev;
   if (S == 0 || B == 0) return cudaSuccess;
   const int Ntot = S * kH;
   dim3 grid((Ntot + BN - 1) / BN, (unsigned)((B + BM - 1) / BM));
@@ -168,7 +170,7 @@ cudaError_t launch_condition(const rnf_flow* f, const float* feat, int64_t B, fl
                                           m.n_mobius_slots, m.n_affine_slots, row_index, count);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (m.n_affine_slots > 0) {
+  if (n_aff_dev > 0) {
     dim3 g2((unsigned)B, m.n_affine_slots);
     cond_affine_kernel<<<g2, 64, 0, st>>>(f->weights_dev + m.caff_off, cond, f->cond_floats, m.n_mobius_slots,
                                           m.n_affine_slots, m.affine_is_rot, count);

@@ -19,6 +19,7 @@
 // piece have completed -- so weight traffic overlaps the mixture math.
 #include "mobius_pair.cuh"
 #include "tc_common.cuh"
+#include "ablation_layers.cuh"
 
 namespace rnf {
 namespace {
@@ -217,11 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
         const float* W = L.cond_slot >= 0 ? cond_img + (int64_t)a.n_mobius_slots * kH + (int64_t)L.cond_slot * kAffFloats
                                           : a.weights + L.w_off;
         if (INV) W += kAffInv;
-        float Wr[17];
-#pragma unroll
-        for (int i = 0; i < 17; ++i) Wr[i] = __ldg(W + i);
-        const float loglen = quat_affine_fast(Wr, R);
-        if (L.has_ldj) ldj += Wr[16] - 4.0f * loglen;
+        affine_family_layer<true>(L, W, R, ldj);
         continue;
       }
       // ================================ Mobius layer ================================
@@ -396,6 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
           return hsum(Fs2) / S_sp - ys;                // the reference's f(x0), same arithmetic for every use
         };
         float lo = kPi / 2.0f, hi = 1.5f * kPi, x0 = 0.0f;
+        int n_eval = 0;                               // evaluations of F by this warp in this layer (measurement hook)
 #if RNF_INV_NEWTON
         // The 15 sign tests of the reference are tests of x0 against the root t* of F: every theta_k(t) is an increasing circle
         // map that stays within +-2 asin(0.7) of t (|w'| < 0.7), so on the bracket F is continuous and strictly increasing
@@ -414,6 +412,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
           for (int it = 0; it < 10; ++it) {
             float dF;
             const float F = probe(ts, dF);
+            ++n_eval;
             if (!conv) {
               if (F < 0.0f) a_ = ts; else b_ = ts;
               dFs = dF;
@@ -436,6 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
             if (__any_sync(0xffffffffu, amb)) {
               float dF;
               const float fx0 = probe(x0, dF);
+              ++n_eval;
               if (amb) neg = fx0 < 0.0f;
             }
             const float half_w = (hi - lo) / 2.0f;
@@ -450,11 +450,13 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
             x0 = (lo + hi) / 2.0f;
             float dF;
             const float fx0 = probe(x0, dF);
+            ++n_eval;
             const float half_w = (hi - lo) / 2.0f;
             if (fx0 < 0.0f) lo = lo + half_w;
             else if (fx0 >= 0.0f) hi = hi - half_w;
           }
         }
+        if (a.probe_counter != nullptr && lane == 0) atomicAdd(a.probe_counter, 32ull * (unsigned long long)n_eval);
         float sn, cs;
         sincos_2pi(x0, sn, cs);
         nx[0] = fmaf(P.v[0], sn, P.r[0] * cs);

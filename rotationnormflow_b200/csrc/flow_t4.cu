@@ -19,6 +19,7 @@
 // The bisection of Flow.inverse needs its 256 prepared parameters resident per row and stays in flow_row.cu.
 #include "mobius_pair.cuh"
 #include "tc_common.cuh"
+#include "ablation_layers.cuh"
 
 namespace rnf {
 namespace {
@@ -127,6 +128,14 @@ __device__ __forceinline__ void relu_split_pair(float x0, float x1, uint32_t& hi
       "}\n"
       : "=f"(d0), "=f"(d1)
       : "r"(hi), "f"(x0), "f"(x1));
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
+#elif RNF_T4_SPLIT_MASK == 2
+  // mixed: one value by the mask (ALU pipe), the other by the conversion (FMA pipe) -- ncu r02: ALU 40 %, FMA 23 % with both on the ALU
+  asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float m0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
+  const float m1 = __high2float(*reinterpret_cast<const __half2*>(&hi));
+  float d0, d1;
+  upk(sub2(pk(x0, x1), pk(m0, m1)), d0, d1);
   asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
 #elif RNF_T4_SPLIT_MASK
   // The fp16 truncation of x, back in fp32, is x with its low 13 mantissa bits cleared: two LOP3 on the (half idle) ALU pipe
@@ -336,11 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
       if (L.kind != RNF_LAYER_MOBIUS) {
         const float* W = L.cond_slot >= 0 ? cond_img + (int64_t)a.n_mobius_slots * kH + (int64_t)L.cond_slot * kAffFloats
                                           : a.weights + L.w_off;
-        float Wr[17];
-#pragma unroll
-        for (int i = 0; i < 17; ++i) Wr[i] = __ldg(W + i);
-        const float loglen = quat_affine_fast(Wr, R);
-        if (L.has_ldj) ldj += Wr[16] - 4.0f * loglen;
+        affine_family_layer<true>(L, W, R, ldj);
         continue;
       }
       // ================================ Mobius layer ================================

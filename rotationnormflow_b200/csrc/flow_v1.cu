@@ -14,6 +14,7 @@
 // flow_t4.cu / flow_row.cu and is validated against this one and against the CPU oracle.
 #include "mobius_math.cuh"
 #include "rnf_common.cuh"
+#include "ablation_layers.cuh"
 
 namespace rnf {
 
@@ -243,11 +244,7 @@ __global__ void __launch_bounds__(T, 1) flow_v1_kernel(const FlowArgs a) {
         const float* W = L.cond_slot >= 0 ? cond_img + (int64_t)a.n_mobius_slots * kH + (int64_t)L.cond_slot * kAffFloats
                                           : a.weights + L.w_off;
         if (INV) W += kAffInv;
-        float Wr[17];
-#pragma unroll
-        for (int i = 0; i < 17; ++i) Wr[i] = __ldg(W + i);
-        const float loglen = quat_affine(Wr, R);
-        if (L.has_ldj) ldj += Wr[16] - 4.0f * loglen;
+        affine_family_layer<false>(L, W, R, ldj);
       }
     }
 

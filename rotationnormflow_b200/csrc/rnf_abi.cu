@@ -24,6 +24,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 long long* g_trace = nullptr;
+unsigned long long* g_probe_counter = nullptr;
 
 bool valid_mode(int m) { return m == RNF_MLP_FP32 || m == RNF_MLP_TC || m == RNF_MLP_TC_ROW; }
 
@@ -39,6 +40,9 @@ extern "C" {
 
 // debug hook (not part of the ABI header): device buffer that -DRNF_TC_TRACE builds fill with clock64() stamps
 void rnf_debug_set_trace(long long* dev_ptr) { g_trace = dev_ptr; }
+// measurement hook (not part of the ABI header; bench.py): device counter that the inverse kernel increments by 32 per warp,
+// Mobius layer and evaluation of the mixture map F, i.e. by the number of (sample, layer, evaluation) triples executed
+void rnf_debug_set_probe_counter(unsigned long long* dev_ptr) { g_probe_counter = dev_ptr; }
 
 int rnf_abi_version(void) { return RNF_ABI_VERSION; }
 
@@ -80,7 +84,7 @@ int rnf_flow_create(const rnf_model_desc* model, const rnf_layer_desc* layers, c
   int n_mob = 0, n_aff = 0;
   for (int i = 0; i < model->n_layers; ++i) {
     const rnf_layer_desc& L = layers[i];
-    if (L.kind != RNF_LAYER_MOBIUS && L.kind != RNF_LAYER_AFFINE) return fail(RNF_EINVAL, "layer %d: bad kind %d", i, L.kind);
+    if (L.kind < RNF_LAYER_MOBIUS || L.kind > RNF_LAYER_RIGHT9) return fail(RNF_EINVAL, "layer %d: bad kind %d", i, L.kind);
     if (L.kind == RNF_LAYER_MOBIUS && (L.perm < 0 || L.perm > 2)) return fail(RNF_EINVAL, "layer %d: bad perm %d", i, L.perm);
     if (L.w_off < 0 || (L.w_off & 3) || L.w_off > model->n_floats) return fail(RNF_EINVAL, "layer %d: bad weight offset", i);
     if (L.cond_slot >= 0) {
@@ -208,6 +212,7 @@ static int run_rows(rnf_flow* f, bool inverse, const float* R_in, int64_t N, con
   a.ldj_out = ldj_out;
   a.scratch = scratch;
   a.trace = g_trace;
+  a.probe_counter = g_probe_counter;
   cudaError_t e;
   if (mlp_mode != RNF_MLP_FP32) {
     if (!rnf::flow_tc_supported(f)) return fail(RNF_ESTATE, "%s: model was packed without the tensor-core weight image", who);
@@ -291,6 +296,7 @@ int rnf_grid_logprob_spread(rnf_flow* f, const float* grid_dev, int64_t G, int64
   a.gt = gt_dev;
   a.gt_k = gt_k;
   a.trace = g_trace;
+  a.probe_counter = g_probe_counter;
   cudaError_t e;
   if (mlp_mode != RNF_MLP_FP32) {
     if (!rnf::flow_tc_supported(f)) return fail(RNF_ESTATE, "rnf_grid_logprob: model was packed without the tensor-core weight image");
@@ -345,6 +351,50 @@ int rnf_min_geodesic(const float* est_dev, const float* gt_dev, int64_t B, int64
   if (!est_dev || !gt_dev || !out_dev) return fail(RNF_EINVAL, "rnf_min_geodesic: null buffer");
   cudaError_t e = rnf::launch_min_geodesic(est_dev, gt_dev, B, K, out_dev, (cudaStream_t)stream);
   return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_min_geodesic");
+}
+
+int rnf_train_max_components(void) { return rnf::train_max_components(); }
+
+static int train_args_ok(const char* who, int64_t N, int K, int perm) {
+  if (N < 0) return fail(RNF_EINVAL, "%s: negative N", who);
+  if (K < 1 || K > rnf::train_max_components()) return fail(RNF_ESHAPE, "%s: K=%d mixture components (1..%d supported)", who, K, rnf::train_max_components());
+  if (perm < 0 || perm > 2) return fail(RNF_EINVAL, "%s: perm must be 0, 1 or 2", who);
+  return rnf_device_check(nullptr);
+}
+
+int rnf_train_mobius_forward(const float* R, const float* out, int64_t N, int K, int perm, int inverse, float* R_out, float* ldj, float* theta,
+                             void* stream) {
+  int rc = train_args_ok("rnf_train_mobius_forward", N, K, perm);
+  if (rc != RNF_OK) return rc;
+  if (N > 0 && (!R || !out || !R_out || !ldj || !theta)) return fail(RNF_EINVAL, "rnf_train_mobius_forward: null buffer");
+  cudaError_t e = rnf::launch_train_mobius_fwd(R, out, N, K, perm, inverse != 0, R_out, ldj, theta, (cudaStream_t)stream);
+  return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_train_mobius_forward");
+}
+
+int rnf_train_mobius_backward(const float* R, const float* out, int64_t N, int K, int perm, int inverse, const float* theta, const float* R_out,
+                              const float* G_Rout, const float* g_ldj, float* G_R, float* G_out, void* stream) {
+  int rc = train_args_ok("rnf_train_mobius_backward", N, K, perm);
+  if (rc != RNF_OK) return rc;
+  if (N > 0 && (!R || !out || !theta || !R_out || !G_Rout || !g_ldj || !G_R || !G_out)) return fail(RNF_EINVAL, "rnf_train_mobius_backward: null buffer");
+  cudaError_t e = rnf::launch_train_mobius_bwd(R, out, N, K, perm, inverse != 0, theta, R_out, G_Rout, g_ldj, G_R, G_out, (cudaStream_t)stream);
+  return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_train_mobius_backward");
+}
+
+int rnf_train_affine_forward(const float* R, const float* W, int64_t N, float* R_out, float* loglen, void* stream) {
+  int rc = train_args_ok("rnf_train_affine_forward", N, 1, 0);
+  if (rc != RNF_OK) return rc;
+  if (N > 0 && (!R || !W || !R_out || !loglen)) return fail(RNF_EINVAL, "rnf_train_affine_forward: null buffer");
+  cudaError_t e = rnf::launch_train_affine_fwd(R, W, N, R_out, loglen, (cudaStream_t)stream);
+  return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_train_affine_forward");
+}
+
+int rnf_train_affine_backward(const float* R, const float* W, int64_t N, const float* R_out, const float* G_Rout, const float* g_loglen,
+                              float* G_R, float* G_W, void* stream) {
+  int rc = train_args_ok("rnf_train_affine_backward", N, 1, 0);
+  if (rc != RNF_OK) return rc;
+  if (N > 0 && (!R || !W || !R_out || !G_Rout || !g_loglen || !G_R || !G_W)) return fail(RNF_EINVAL, "rnf_train_affine_backward: null buffer");
+  cudaError_t e = rnf::launch_train_affine_bwd(R, W, N, R_out, G_Rout, g_loglen, G_R, G_W, (cudaStream_t)stream);
+  return e == cudaSuccess ? RNF_OK : cuda_fail(e, "rnf_train_affine_backward");
 }
 
 }  // extern "C"

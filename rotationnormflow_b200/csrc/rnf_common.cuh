@@ -23,8 +23,8 @@ constexpr int kMobFloats = kMobLast + kH * 4 * kK + 4 * kK;  // 29376 floats = 1
 
 // ---- affine block (unconditional in the weight buffer, conditional per image in the cond buffer) -----------
 //   [0..15] W, [16] log|det W|, [20..35] W^-1 (or W^T for rotation layers), [36] log|det W^-1|
-constexpr int kAffFloats = 40;
-constexpr int kAffInv = 20;
+constexpr int kAffFloats = RNF_AFFINE_BLOCK_FLOATS;
+constexpr int kAffInv = 40;
 
 // ---- conditional-affine MLP tail block (per slot, at model.caff_off + slot*kCaffFloats) ---------------------
 //   b_first[64], 3 x (W[64 out][64 in] row-major as in nn.Linear, b[64]), W_last[16][64], b_last[16]
@@ -68,6 +68,7 @@ struct FlowArgs {
   float* part;        // [n_tiles][kPartStride]: (max, sum exp(lp - max), argmax lo, argmax hi, sum exp(lp - max) * d_gt, -, -, -)
   const float* gt;    // [B][gt_k][9] ground-truth rotations per image (spread metric), nullptr = not requested
   int gt_k;
+  unsigned long long* probe_counter;   // measurement hook (rnf_debug_set_probe_counter), normally null
   long long* trace;   // debug builds (-DRNF_TC_TRACE): per-phase clock64() stamps of CTA 0, else unused
 };
 
@@ -95,6 +96,14 @@ size_t dedup_scan_bytes(int64_t N);
 cudaError_t launch_dedup(const float* feat, int64_t N, int64_t F, int32_t* idx, int32_t* first, int64_t cap, int32_t* count, void* ws,
                          size_t ws_bytes, int sm_count, cudaStream_t st);
 cudaError_t launch_poison(const int32_t* count, int64_t cap, float* ldj, int64_t N, cudaStream_t st);
+cudaError_t launch_train_mobius_fwd(const float* R, const float* out, int64_t N, int K, int perm, bool inverse, float* R_out, float* ldj,
+                                    float* theta, cudaStream_t st);
+cudaError_t launch_train_mobius_bwd(const float* R, const float* out, int64_t N, int K, int perm, bool inverse, const float* theta,
+                                    const float* R_out, const float* G_Rout, const float* g_ldj, float* G_R, float* G_out, cudaStream_t st);
+cudaError_t launch_train_affine_fwd(const float* R, const float* W, int64_t N, float* R_out, float* loglen, cudaStream_t st);
+cudaError_t launch_train_affine_bwd(const float* R, const float* W, int64_t N, const float* R_out, const float* G_Rout, const float* g_loglen,
+                                    float* G_R, float* G_W, cudaStream_t st);
+int train_max_components();
 cudaError_t launch_healpix(int level, int64_t begin, int64_t end, float* out, cudaStream_t st);
 cudaError_t launch_min_geodesic(const float* est, const float* gt, int64_t B, int64_t K, float* out, cudaStream_t st);
 cudaError_t launch_fisher_logprob(const float* A9, const float* c, const float* R, int64_t N, int64_t rows_per_image, float* out,

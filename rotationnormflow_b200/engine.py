@@ -19,8 +19,8 @@ HIDDEN = 64       # flow/condition.py:9 (Nh)
 
 # float sizes of the packed blocks; must mirror csrc/rnf_common.cuh
 MOB_FLOATS = 64 * 4 + 3 * (64 * 64 + 64) + 64 * 256 + 256
-AFF_FLOATS = 40
-AFF_INV = 20
+AFF_FLOATS = 80          # RNF_AFFINE_BLOCK_FLOATS: forward block [0,40), inverse-direction block [40,80)
+AFF_INV = 40
 CAFF_FLOATS = 64 + 3 * (64 * 64 + 64) + 16 * 64 + 16
 
 TC_AVAILABLE = True    # csrc/flow_t4.cu (forward, grid) + csrc/flow_row.cu (inverse): tcgen05 conditioner
@@ -191,6 +191,48 @@ def pack_affine_matrix(W: torch.Tensor, is_rot: bool) -> np.ndarray:
     return blk
 
 
+ABLATION_KINDS = {"smith9": _cabi.RNF_LAYER_SMITH9, "smith36": _cabi.RNF_LAYER_SMITH36, "polar9l": _cabi.RNF_LAYER_POLAR9L,
+                  "polar9r": _cabi.RNF_LAYER_POLAR9R, "right9": _cabi.RNF_LAYER_RIGHT9}
+
+
+def gram_schmidt_columns(M: torch.Tensor) -> torch.Tensor:
+    """Q of calculate_9_r_smith (flow/rottrans.py:82-88): Gram-Schmidt of the first two columns of M [...,3,3], third = cross."""
+    c0 = M[..., 0] / M[..., 0].norm(dim=-1, keepdim=True)
+    c1 = M[..., 1] - (c0 * M[..., 1]).sum(dim=-1, keepdim=True) * c0
+    c1 = c1 / c1.norm(dim=-1, keepdim=True)
+    return torch.stack([c0, c1, torch.linalg.cross(c0, c1, dim=-1)], dim=-1)
+
+
+def ablation_blocks(kind: str, M: torch.Tensor) -> torch.Tensor:
+    """Matrices M [B,n,n] of an ablation layer -> parameter blocks [B, AFF_FLOATS]: what the layer applies in the forward direction
+    at [0, n*n) and in the inverse direction at [AFF_INV, AFF_INV + n*n) -- torch.linalg.inv(M) for the Smith layers
+    (flow/squeezetrans.py:245,260,347,360), M^T for the SVD layers (flow/rottrans.py:103,119), Q / Q^T of the Gram-Schmidt
+    for the right-multiplied rotation (flow/rottrans.py:81-91).  Per-layer / per-image parameter algebra, not a per-rotation path."""
+    B, n = M.shape[0], M.shape[-1]
+    if kind in ("smith9", "smith36"):
+        fwd, inv = M, torch.linalg.inv(M)
+    elif kind in ("polar9l", "polar9r"):
+        fwd, inv = M, M.transpose(-1, -2)
+    else:
+        fwd = gram_schmidt_columns(M)
+        inv = fwd.transpose(-1, -2)
+    blk = torch.zeros((B, AFF_FLOATS), dtype=torch.float32, device=M.device)
+    blk[:, :n * n] = fwd.reshape(B, -1).to(torch.float32)
+    blk[:, AFF_INV:AFF_INV + n * n] = inv.reshape(B, -1).to(torch.float32)
+    return blk
+
+
+def conditioner_torch(ct, x: torch.Tensor) -> torch.Tensor:
+    """ConditionalTransform.forward (flow/condition.py:24-30) on PER-IMAGE inputs x [B,Ni], as plain library GEMMs (the ablation
+    layers' 3x3 / 6x6 matrix networks: B rows, never the per-rotation path)."""
+    lin = torch.nn.functional.linear
+    h0 = lin(x, ct.fc_first.weight, ct.fc_first.bias)
+    h = h0
+    for j in (1, 3, 5):
+        h = lin(torch.relu(h), ct.layers[j].weight, ct.layers[j].bias)
+    return lin(torch.relu(h0 + h), ct.fc_last.weight, ct.fc_last.bias)
+
+
 def pack_cond_affine(net_sd: dict, F: int) -> tuple[np.ndarray, np.ndarray]:
     """ConditionalTransform(F, 16) -> (tail block [CAFF_FLOATS], W_f [64,F])."""
     W0, b0 = _np(net_sd["fc_first.weight"]), _np(net_sd["fc_first.bias"])
@@ -236,9 +278,11 @@ def layer_tensors(layer) -> list:
         return [layer.mat]
     if layer.kind == "rot_u":
         return [layer.rot]
-    if layer.kind == "aff_lu":
+    if layer.kind == "aff_lu" or (layer.kind.endswith("_u") and isinstance(getattr(layer, "mat", None), torch.nn.Module)):
         m = layer.mat
         return [m.w_p, m.u_mask, m.l_mask, m.s_sign, m.l_eye, m.w_l, m.w_s, m.w_u]
+    if layer.kind.split("_")[0] in ABLATION_KINDS:
+        return list(conditioner_tensors(layer.net).values()) if layer.kind.endswith("_c") else [layer.mat]
     return [t for t in list(layer.parameters()) + list(layer.buffers())]
 
 
@@ -267,6 +311,7 @@ class Program:
         descs = (_cabi.LayerDesc * max(1, len(specs)))()
         wf_mob, wf_aff, caff = [], [], []
         self.rot_slots: list = []          # modules of conditional rotation layers, slot order
+        self.ablation_slots: list = []     # (kind, module) of conditional ablation layers, slot order
         n_mob = n_aff = 0
         cond_kinds = set()
         for i, s in enumerate(specs):
@@ -286,6 +331,19 @@ class Program:
                     d.cond_slot = n_mob
                     n_mob += 1
                     wf_mob.append(wf)
+            elif s.kind.split("_")[0] in ABLATION_KINDS:
+                base_kind = s.kind.split("_")[0]
+                d.kind = ABLATION_KINDS[base_kind]
+                d.has_ldj = 1 if base_kind.startswith("smith") else 0
+                if s.kind.endswith("_c"):
+                    cond_kinds.add("ablation")
+                    d.cond_slot = n_aff
+                    n_aff += 1
+                    self.ablation_slots.append((base_kind, s.module))
+                else:
+                    with torch.no_grad():
+                        M = s.module.matrix().detach().to("cpu", torch.float64)
+                        d.w_off = push(ablation_blocks(base_kind, M.reshape(1, M.shape[-1], M.shape[-1])).numpy())
             else:
                 d.kind = _cabi.RNF_LAYER_AFFINE
                 d.has_ldj = 0 if s.kind.startswith("rot") else 1
@@ -301,13 +359,13 @@ class Program:
                 else:
                     d.w_off = push(pack_affine_matrix(s.module.matrix(), is_rot=(s.kind == "rot_u")))
         if len(cond_kinds) > 1:
-            raise NotImplementedError("mixing Condition16Trans and ConditionRot layers in one flow")
+            raise NotImplementedError("mixing different families of conditional affine layers in one flow")
         model = _cabi.ModelDesc()
         model.abi_version = _cabi.ABI_VERSION
         model.n_layers = len(specs)
         model.K, model.H, model.F = K_SEGMENTS, HIDDEN, self.F
         model.n_mobius_slots, model.n_affine_slots = n_mob, n_aff
-        model.affine_is_rot = 1 if "rot_c" in cond_kinds else 0
+        model.affine_is_rot = 1 if "rot_c" in cond_kinds else (2 if "ablation" in cond_kinds else 0)
         model.wf_off = push(np.concatenate([w.reshape(-1) for w in wf_mob + wf_aff])) if (wf_mob or wf_aff) else 0
         model.caff_off = push(np.concatenate(caff)) if caff else 0
         if not blocks:
@@ -349,7 +407,21 @@ class Program:
                                                     C.c_void_p(cond.data_ptr()), self._stream()))
         if self.rot_slots:
             self._polar_factor(cond, B)
+        if self.ablation_slots:
+            self._fill_ablation_slots(cond, feat)
         return cond
+
+    def _fill_ablation_slots(self, cond: torch.Tensor, feat_rows: torch.Tensor) -> None:
+        """Conditional ablation layers (Condition9Trans, Condition36Trans, Condition9Rot*; flow/squeezetrans.py:235-247,334-347,
+        flow/rottrans.py:107-181): M = MLP(feature).reshape(n,n) + I per IMAGE, written into the slots' parameter blocks."""
+        base = self.n_mob * HIDDEN
+        B = cond.shape[0]
+        blk = cond[:, base: base + self.n_aff * AFF_FLOATS].view(B, self.n_aff, AFF_FLOATS)
+        with torch.no_grad():
+            for slot, (kind, module) in enumerate(self.ablation_slots):
+                n = 6 if kind == "smith36" else 3
+                M = conditioner_torch(module.net, feat_rows).reshape(B, n, n) + torch.eye(n, device=cond.device)
+                blk[:, slot] = ablation_blocks(kind, M)
 
     def _polar_factor(self, cond: torch.Tensor, B: int) -> None:
         """ConditionRot (flow/rottrans.py:43-46,55-58): rot = U^T V with (U,S,V) = torch.svd(MLP(feature)+I), in place.
@@ -381,6 +453,8 @@ class Program:
                                                          C.c_void_p(count.data_ptr()), cap, C.c_void_p(cond.data_ptr()), self._stream()))
         if self.rot_slots:
             self._polar_factor(cond, cap)
+        if self.ablation_slots:
+            self._fill_ablation_slots(cond, feat[first.long()])      # rows beyond the run count read row 0: never indexed
         return cond
 
     def poison_if_overflow(self, count: torch.Tensor, cap: int, ldj: torch.Tensor) -> None:

@@ -93,8 +93,9 @@ class MobiusFlow(_FusedLayer):
         super().__init__()
         if D != 3:
             raise ValueError("MobiusFlow acts on columns of a 3x3 rotation: D must be 3")
-        if K != engine.K_SEGMENTS:
-            raise NotImplementedError(f"the sm_100a kernels are specialised for segments={engine.K_SEGMENTS} (every settings/*.yml); got {K}")
+        if K < 1:
+            raise ValueError("MobiusFlow needs at least one mixture component")
+        # K = 64 (every settings/*.yml) runs in the fused tcgen05 kernels; any other K in the per-layer operators of train.py
         self.D, self.K = D, K
         self.condition = condition
         self.feature_dim = feature_dim
@@ -221,13 +222,95 @@ class ConditionRot(_FusedLayer):
         return self.feature_dim
 
 
-_OUT_OF_SCOPE = {
-    "36Trans": "Condition36Trans/Uncondition36Trans (flow/squeezetrans.py:200-361)",
-    "9TransLSVD": "Condition9RotL/Uncondition9RotL (flow/rottrans.py:69-181)",
-    "9TransRSVD": "Condition9RotR/Uncondition9RotR (flow/rottrans.py:69-181)",
-    "9TransLSmith": "Condition9Trans/Uncondition9Trans (flow/squeezetrans.py:177-361)",
-    "9TransRSmith": "Condition9RotRSmith/Uncondition9RotRSmith (flow/rottrans.py:69-181)",
-}
+class _AblationUncond(_FusedLayer):
+    """Unconditional ablation layer: a free n x n matrix ``mat`` (init I + 1e-3 randn), reference state-dict key ``mat``."""
+
+    n = 3
+
+    def __init__(self):
+        super().__init__()
+        self.mat = nn.Parameter(torch.eye(self.n) + torch.randn(self.n, self.n) * 1e-3)
+
+    def matrix(self):
+        return self.mat
+
+
+class _AblationCond(_FusedLayer):
+    """Conditional ablation layer: ``net`` = ConditionalTransform(feature_dim, n*n); M = net(feature).reshape(n,n) + I per image."""
+
+    n = 3
+    uses_feature = True
+
+    def __init__(self, feature_dim):
+        super().__init__()
+        self.feature_dim = feature_dim
+        self.net = ConditionalTransform(feature_dim, self.n * self.n)
+
+    def _feature_dim(self):
+        return self.feature_dim
+
+
+class Uncondition9Trans(_AblationUncond):
+    """flow/squeezetrans.py:250-262 (calculate_9: Gram-Schmidt of M R with its log-det)."""
+    kind = "smith9_u"
+
+
+class Condition9Trans(_AblationCond):
+    """flow/squeezetrans.py:235-247."""
+    kind = "smith9_c"
+
+
+class Uncondition9TransLU(_FusedLayer):
+    """flow/squeezetrans.py:279-291: calculate_9 with the PLU-parameterised 3x3."""
+    kind = "smith9_u"
+
+    def __init__(self):
+        super().__init__()
+        self.mat = UnconditionLU(3)
+
+    def matrix(self):
+        with torch.no_grad():
+            return self.mat()
+
+
+class Uncondition36Trans(_AblationUncond):
+    """flow/squeezetrans.py:350-361 (calculate_36: 6x6 matrix on the 6-D representation)."""
+    kind, n = "smith36_u", 6
+
+
+class Condition36Trans(_AblationCond):
+    """flow/squeezetrans.py:334-347."""
+    kind, n = "smith36_c", 6
+
+
+class Uncondition9RotL(_AblationUncond):
+    """flow/rottrans.py:94-105 (calculate_9_l: polar factor of M R; the inverse direction uses M^T, as the reference does)."""
+    kind = "polar9l_u"
+
+
+class Condition9RotL(_AblationCond):
+    """flow/rottrans.py:107-121."""
+    kind = "polar9l_c"
+
+
+class Uncondition9RotR(_AblationUncond):
+    """flow/rottrans.py:124-135 (calculate_9_r: polar factor of R M)."""
+    kind = "polar9r_u"
+
+
+class Condition9RotR(_AblationCond):
+    """flow/rottrans.py:138-151."""
+    kind = "polar9r_c"
+
+
+class Uncondition9RotRSmith(_AblationUncond):
+    """flow/rottrans.py:154-165 (calculate_9_r_smith: R Q, Q = Gram-Schmidt of M)."""
+    kind = "right9_u"
+
+
+class Condition9RotRSmith(_AblationCond):
+    """flow/rottrans.py:168-181."""
+    kind = "right9_c"
 
 
 def get_mobius(config, feature_dim):
@@ -238,26 +321,35 @@ def get_mobius(config, feature_dim):
 
 
 def get_affine(config, feature_dim, first_layer_condition=False):
-    """Dispatch table of flow/affineflow.py:5-73 for the layer families on the hot path."""
+    """Dispatch table of flow/affineflow.py:5-73."""
     rot, lu = config.rot, bool(getattr(config, "lu", 0))
 
-    def lu_conditional():
+    def lu_conditional(n):
         raise NotImplementedError(
-            "Condition16TransLU (flow/squeezetrans.py:94-144) is batch-coupled in the reference (torch.diag on a [N,4] "
-            "tensor) and is outside the hot-path scope (SURVEY.md section 2 row 5)")
+            f"Condition{n * n}TransLU (flow/squeezetrans.py:94-144,265-277) is batch-coupled in the reference (ConditionLU applies "
+            "torch.diag to a [N,n] tensor, which returns a diagonal instead of building one per row); there is no well-defined "
+            "per-rotation function to reproduce")
 
     if first_layer_condition:
         if rot == "16UnTrans":
-            return lu_conditional() if lu else Condition16Trans(feature_dim)
+            return lu_conditional(4) if lu else Condition16Trans(feature_dim)
         if rot == "16UnRot":
             return ConditionRot(feature_dim)
-    if rot in _OUT_OF_SCOPE:
-        raise NotImplementedError(f"rot={rot!r}: {_OUT_OF_SCOPE[rot]} is an ablation layer outside the hot-path scope (SURVEY.md 8f N4)")
     if config.condition:
         if rot == "16Trans":
-            return lu_conditional() if lu else Condition16Trans(feature_dim)
+            return lu_conditional(4) if lu else Condition16Trans(feature_dim)
         if rot == "16UnTrans":
             return Uncondition16TransLU() if lu else Uncondition16Trans()
+        if rot == "36Trans":
+            return Condition36Trans(feature_dim)
+        if rot == "9TransLSVD":
+            return Condition9RotL(feature_dim)
+        if rot == "9TransRSVD":
+            return Condition9RotR(feature_dim)
+        if rot == "9TransLSmith":
+            return lu_conditional(3) if lu else Condition9Trans(feature_dim)
+        if rot == "9TransRSmith":
+            return Condition9RotRSmith(feature_dim)
         if rot == "16Rot":
             return ConditionRot(feature_dim)
         if rot == "16UnRot":
@@ -265,6 +357,16 @@ def get_affine(config, feature_dim, first_layer_condition=False):
         return None
     if rot == "16Trans":
         return Uncondition16TransLU() if lu else Uncondition16Trans()
+    if rot == "36Trans":
+        return Uncondition36Trans()
+    if rot == "9TransLSVD":
+        return Uncondition9RotL()
+    if rot == "9TransRSVD":
+        return Uncondition9RotR()
+    if rot == "9TransLSmith":
+        return Uncondition9TransLU() if lu else Uncondition9Trans()
+    if rot == "9TransRSmith":
+        return Uncondition9RotRSmith()
     if rot == "16Rot":
         return UnconditionRot()
     return None
@@ -328,12 +430,37 @@ def _check_rotation(rotation):
         raise ValueError(f"rotation must be a [N,3,3] tensor, got {tuple(getattr(rotation, 'shape', ()))}")
     if not rotation.is_cuda:
         raise RuntimeError("rotationnormflow_b200 runs on a B200 only: `rotation` must be a CUDA tensor (there is no CPU fallback)")
-    if rotation.requires_grad:
-        raise NotImplementedError("autograd through the fused kernels is outside the hot-path scope (inference / evaluation only)")
     return rotation.to(torch.float32).contiguous()
 
 
+def _needs_composed(layers, rotation, feature) -> bool:
+    """True when the call must run layer by layer in the differentiable operators of train.py: autograd is on and something
+    requires grad (the reference builds a graph there: training at agent.py:87, eval.py:468-477), or a Mobius layer has a number of
+    mixture components other than the 64 the fused kernels are specialised for."""
+    if any(l.kind == "mobius" and l.K != engine.K_SEGMENTS for l in layers):
+        return True
+    return _wants_grad(layers, rotation, feature)
+
+
+def _run_composed(layers, perms, rotation, feature, inverse, feature_index):
+    from . import train
+    R = _check_rotation(rotation)
+    conditional = any(getattr(l, "uses_feature", False) or (l.kind == "mobius" and l.condition) for l in layers)
+    rows = None
+    if conditional:
+        if feature is None:
+            raise AssertionError("The input feature is needed in this module")
+        rows = feature.to(R.device, torch.float32)
+        if feature_index is not None:
+            rows = rows[feature_index.to(R.device).long()]
+        if rows.shape[0] != R.shape[0]:
+            raise ValueError(f"feature has {rows.shape[0]} rows for {R.shape[0]} rotations (the reference asserts equality, agent.py:211,259)")
+    return train.composed_run(layers, perms, R, rows, inverse)
+
+
 def _run(layers, perms, F, owner, rotation, feature, inverse, feature_index=None, mode=None):
+    if _needs_composed(layers, rotation, feature):
+        return _run_composed(layers, perms, rotation, feature, inverse, feature_index)
     R = _check_rotation(rotation)
     prog = _program(owner, layers, perms, F, R.device)
     mode = mode or engine.default_mlp_mode()
@@ -343,9 +470,6 @@ def _run(layers, perms, F, owner, rotation, feature, inverse, feature_index=None
         raise AssertionError("The input feature is needed in this module")
     if conditional and feature_index is None and feature.shape[0] != N:
         raise ValueError(f"feature has {feature.shape[0]} rows for {N} rotations (the reference asserts equality, agent.py:211,259)")
-    if _wants_grad(layers, rotation, feature if conditional else None):
-        what = "the rotation" if rotation.requires_grad else ("the feature" if (conditional and feature.requires_grad) else "a flow parameter")
-        raise NotImplementedError(_GRAD_MESSAGE.format(what=what))
     if not conditional:
         return prog.run(R, None, 0, None, 1, inverse, mode)
     feature = feature.to(R.device)

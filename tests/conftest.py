@@ -12,7 +12,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-SMALL_CASES = ["s_uncond", "s_symsol", "s_modelnet", "s_pascal", "s_lu", "s_rot", "s_rotc", "s_unrot", "s_mobonly"]
+ABLATION_CASES = ["s_smith9", "s_smith9lu", "s_smith36", "s_polar9l", "s_polar9r", "s_right9", "s_smith9c", "s_smith36c", "s_polar9lc",
+                  "s_polar9rc", "s_right9c"]      # flow/affineflow.py:27-41,55-70
+# The reference's `inverse` of these layers is not the inverse map of its `forward` (inv(M) on the 6-D representation before the
+# Gram-Schmidt; M^T in place of the inverse for the SVD layers): parity holds per direction, the round-trip property does not.
+NOT_BIJECTIVE = {"s_smith36", "s_smith36c", "s_polar9l", "s_polar9r", "s_polar9lc", "s_polar9rc"}
+SMALL_CASES = ["s_uncond", "s_symsol", "s_modelnet", "s_pascal", "s_lu", "s_rot", "s_rotc", "s_unrot", "s_mobonly"] + ABLATION_CASES
 FULL_CASES = ["raw", "symsol2048", "symsol2", "modelnet"]
 
 

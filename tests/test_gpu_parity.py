@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import FULL_CASES, GOLDEN, SMALL_CASES, golden, record_error, seeded_product_flow
+from conftest import ABLATION_CASES, FULL_CASES, GOLDEN, NOT_BIJECTIVE, SMALL_CASES, golden, record_error, seeded_product_flow
 from oracle import rnf_oracle as orc
 import rotationnormflow_b200 as rnf
 from rotationnormflow_b200 import grid as rgrid
@@ -99,7 +99,10 @@ def test_forward_parity(tag, mode):
     if feat is not None:
         with torch.no_grad():
             R2, l2 = m(g.R.cuda(), g.feat.cuda(), feature_index=g.feat_index.cuda(), mlp_mode=mode)
-        assert torch.equal(R2.cpu().double(), R) and torch.equal(l2.cpu().double(), ldj)
+        # bit-identical -- except for the conditional ablation layers, whose per-image 3x3 / 6x6 matrix networks run as library
+        # GEMMs whose reduction order depends on the number of rows handed over (capacity rows vs B rows)
+        slack = 2e-6 if (tag in ABLATION_CASES and tag.endswith("c")) else 0.0
+        assert (R2.cpu().double() - R).abs().max() <= slack and rel(l2.cpu().double(), ldj) <= 100 * slack
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -136,8 +139,9 @@ def test_inverse_parity(tag, mode):
     # (the random-init F=2080 ModelNet stack amplifies the pi/2^15 angle quantum to 1.4e-2 / 1.8e-2 in the reference
     #  itself, fp32 and fp64 alike -- measured with the oracle -- hence its own bound)
     rt_R, rt_l = {"modelnet": (3e-2, 4e-2)}.get(tag, (max(2e-4 * nmob, 1e-5), max(2e-3 * nmob, 1e-5)))
-    assert (Rf.cpu().double() - g.R.double()).abs().max().item() <= rt_R
-    assert (lf.cpu().double() + lc).abs().max().item() <= rt_l
+    if tag not in NOT_BIJECTIVE:             # (the reference's own `inverse` of those ablation layers is not the inverse map)
+        assert (Rf.cpu().double() - g.R.double()).abs().max().item() <= rt_R
+        assert (lf.cpu().double() + lc).abs().max().item() <= rt_l
     l64 = g.out("inv", "ldj", TRUTH.get(tag, "f64")).double()
     ok = d64 <= 1e-5
     if ok.any():
@@ -617,21 +621,25 @@ def test_drop_in_call_with_repeated_features():
         assert torch.equal(out[0], fresh[0]) and torch.equal(out[1], fresh[1])
 
 
-def test_autograd_is_refused_loudly_and_cache_hygiene():
-    """no silently detached outputs in grad mode; the packed-program cache neither blocks deepcopy / pickle nor
+def test_autograd_dispatch_and_cache_hygiene():
+    """no silently detached outputs in grad mode -- with autograd on and something requiring grad the call runs in the
+    differentiable per-layer operators (tests/test_gpu_train.py); the packed-program cache neither blocks deepcopy / pickle nor
     survives invalidate_cache()."""
     import copy
     import pickle
     g = golden("s_symsol")
     m = _product(g)
     R, rows = g.R.cuda(), g.rows.cuda()
-    with pytest.raises(NotImplementedError, match="no_grad"):
-        m(R, rows)                                                         # parameters require grad, autograd is on
+    Rg, lg = m(R, rows)                                                    # parameters require grad, autograd is on
+    assert lg.requires_grad and lg.grad_fn is not None
     with torch.no_grad():
         a = m(R, rows)
+    assert not a[1].requires_grad and (a[1] - lg.detach()).abs().max() < 1e-4
     fr = rows.clone().requires_grad_(True)
-    with pytest.raises(NotImplementedError, match="feature"):
-        m(R, fr)
+    for p in m.parameters():
+        p.requires_grad_(False)
+    assert m(R, fr)[1].requires_grad                                       # a backbone feature that requires grad is enough
+    assert not m(R, rows)[1].requires_grad                                 # nothing requires grad: the fused kernels
     with pytest.raises(NotImplementedError):
         m.grid_log_prob(rgrid.healpix_grid(0), g.feat.cuda().requires_grad_(True))
     m2 = copy.deepcopy(m)                                                  # after the first call: the cache holds a ctypes handle

@@ -45,12 +45,13 @@ def test_layer_stack_matches_oracle_plan():
 
 
 def test_out_of_scope_layers_raise():
-    with pytest.raises(NotImplementedError):
-        rnf.get_flow(rnf.load_config("raw", rot="36Trans"))
+    # ConditionLU (Condition16TransLU / Condition9TransLU) is batch-coupled in the reference: torch.diag of a [N,n] tensor
     with pytest.raises(NotImplementedError):
         rnf.get_flow(rnf.load_config("modelnet_uni", lu=1))
     with pytest.raises(NotImplementedError):
-        rnf.get_flow(rnf.load_config("raw", segments=32))
+        rnf.get_flow(rnf.load_config("modelnet_uni", rot="9TransLSmith", lu=1))
+    # config.segments != 64 is accepted (it runs in the per-layer operators of train.py, tests/test_gpu_train.py)
+    assert rnf.get_flow(rnf.load_config("raw", segments=32, layers=1)).layers[0].K == 32
 
 
 def test_config_defaults_follow_reference():
@@ -169,11 +170,34 @@ def test_affine_packing():
     W = torch.eye(4) + 0.1 * torch.randn(4, 4, generator=torch.Generator().manual_seed(0))
     blk = engine.pack_affine_matrix(W[None], is_rot=False)
     assert np.allclose(blk[:16].reshape(4, 4), W.numpy())
-    assert np.allclose(blk[20:36].reshape(4, 4) @ W.numpy(), np.eye(4), atol=1e-6)
+    inv = engine.AFF_INV
+    assert blk.size == engine.AFF_FLOATS
+    assert np.allclose(blk[inv:inv + 16].reshape(4, 4) @ W.numpy(), np.eye(4), atol=1e-6)
     assert abs(blk[16] - float(orc.det4(W.double()).abs().log())) < 1e-6
-    assert abs(blk[16] + blk[36]) < 1e-6
+    assert abs(blk[16] + blk[inv + 16]) < 1e-6
     rot = engine.pack_affine_matrix(torch.eye(4)[None], is_rot=True)
-    assert rot[16] == 0 and rot[36] == 0
+    assert rot[16] == 0 and rot[inv + 16] == 0
+
+
+def test_ablation_packing():
+    """Parameter blocks of the ablation layers: forward matrix at 0, inverse-direction matrix at AFF_INV (engine.ablation_blocks)."""
+    g = torch.Generator().manual_seed(1)
+    M3 = torch.eye(3) + 0.2 * torch.randn(2, 3, 3, generator=g)
+    M6 = torch.eye(6) + 0.1 * torch.randn(1, 6, 6, generator=g)
+    inv = engine.AFF_INV
+    b = engine.ablation_blocks("smith9", M3.double())
+    assert torch.allclose(b[:, inv:inv + 9].reshape(2, 3, 3) @ b[:, :9].reshape(2, 3, 3), torch.eye(3).expand(2, 3, 3), atol=1e-6)
+    b = engine.ablation_blocks("smith36", M6.double())
+    assert torch.allclose(b[:, inv:inv + 36].reshape(1, 6, 6) @ M6, torch.eye(6)[None], atol=1e-6)
+    b = engine.ablation_blocks("polar9l", M3)
+    assert torch.equal(b[:, inv:inv + 9].reshape(2, 3, 3), M3.transpose(1, 2))
+    b = engine.ablation_blocks("right9", M3)
+    Q = b[:, :9].reshape(2, 3, 3)
+    assert torch.allclose(Q @ Q.transpose(1, 2), torch.eye(3).expand(2, 3, 3), atol=1e-6) and (torch.linalg.det(Q) - 1).abs().max() < 1e-5
+    assert torch.equal(b[:, inv:inv + 9].reshape(2, 3, 3), Q.transpose(1, 2))
+    # the restatement of calculate_9_r_smith in the oracle builds the same Q
+    R = orc.random_rotations(2, g)
+    assert torch.allclose(orc.right9(M3, R, False)[0], R @ Q, atol=1e-6)
 
 
 def test_cabi_exports_every_declared_symbol():

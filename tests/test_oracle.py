@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import FULL_CASES, GOLDEN, SMALL_CASES, golden
+from conftest import FULL_CASES, GOLDEN, NOT_BIJECTIVE, SMALL_CASES, golden
 from oracle import rnf_oracle as orc
 from oracle import stubs
 
@@ -39,6 +39,8 @@ def test_inverse_matches_golden(tag):
     # bisection branch decisions are identical in fp64 -> same dyadic angles
     assert (R - g.out("inv", "R", "f64")).abs().max() < 1e-9
     assert (ldj - g.out("inv", "ldj", "f64")).abs().max() < 1e-9
+    if tag in NOT_BIJECTIVE:
+        return
     # round trip to bisection resolution (pi / 2^15 per Mobius layer) and ldj_inv = -ldj_fwd
     Rf, lf = o64.forward(R, g.rows)
     nmob = sum(k == "mobius" for k in o64.plan)
@@ -159,6 +161,48 @@ def test_oracle_against_live_reference():
         Rr, lr = rl.run_reference(m, R, feat, inverse=inv)
         Ro, lo = (o.inverse if inv else o.forward)(R, feat)
         assert (Rr - Ro).abs().max() < 1e-9 and (lr - lo).abs().max() < 1e-9
+
+
+def _grad_loss(R, ldj, A, c):
+    return (A * R).sum() + (c * ldj).sum()
+
+
+def test_oracle_gradients_against_live_reference():
+    """Autograd through the restatement == autograd through the unmodified reference, forward (training, agent.py:87) and inverse
+    (BinFind.backward, flow/mobiusflow.py:248-273): parameter, feature and rotation gradients in fp64."""
+    from oracle import ref_loader as rl
+    if not rl.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    for cfg_name, ov in (("symsol", dict(layers=2, feature_dim=16)), ("modelnet_uni", dict(layers=2, feature_dim=8, embedding=0)), ("raw", dict(layers=2))):
+        cfg = rl.ref_config(cfg_name, **ov)
+        m = rl.build_reference_flow(cfg, 33, torch.float64)
+        gen = torch.Generator().manual_seed(6)
+        N = 24
+        F = orc.feature_dim_of(cfg)
+        A = torch.randn(N, 3, 3, generator=gen, dtype=torch.float64)
+        c = torch.randn(N, generator=gen, dtype=torch.float64)
+        for inv in (False, True):
+            R = orc.random_rotations(N, gen, torch.float64).requires_grad_(True)
+            feat = torch.randn(N, F, generator=gen, dtype=torch.float64).requires_grad_(True) if F else None
+            m.zero_grad()
+            with rl.default_dtype(torch.float64):
+                Rr, lr = (m.inverse if inv else m)(R, feat)
+                _grad_loss(Rr, lr, A, c).backward()
+            ref = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+            ref_R, ref_f = R.grad.clone(), (None if feat is None else feat.grad.clone())
+            o = orc.OracleFlow(cfg, m.state_dict(), torch.float64)
+            for k in ref:
+                o.sd[k] = o.sd[k].clone().requires_grad_(True)
+            R2 = R.detach().clone().requires_grad_(True)
+            f2 = None if feat is None else feat.detach().clone().requires_grad_(True)
+            Ro, lo = o.with_grad(R2, f2, inverse=inv)
+            _grad_loss(Ro, lo, A, c).backward()
+            assert ref, "the reference produced no parameter gradients"
+            for k, g in ref.items():
+                assert (o.sd[k].grad - g).abs().max() <= 1e-8 * max(1.0, g.abs().max().item()), (cfg_name, inv, k)
+            assert (R2.grad - ref_R).abs().max() < 1e-8
+            if feat is not None:
+                assert (f2.grad - ref_f).abs().max() < 1e-8
 
 
 def test_geodesic_metric_against_live_reference():

@@ -8,7 +8,7 @@ import bench
 from rotationnormflow_b200 import grid as rgrid
 
 mode = os.environ.get("MODE", "tc")
-cfg, flow = bench.build_flow()
+cfg, flow = bench.build_flow("symsol", feature_dim=2048)
 flow = flow.cuda().eval()
 G = rgrid.healpix_grid(5)
 feat = torch.relu(torch.randn(1, 2048)).cuda()

@@ -15,6 +15,7 @@ base = rgrid.generate_queries(n_img * n_per, "random", device="cuda")
 feat = torch.relu(torch.randn(n_img, 512)).cuda()
 idx = torch.arange(n_img * n_per, device="cuda", dtype=torch.int32) // n_per
 for _ in range(2):
+  with torch.no_grad():
     R, l = flow.inverse(base, feat, feature_index=idx, mlp_mode=os.environ.get("MODE", "tc"))
 torch.cuda.synchronize()
 print(R.shape, float(l.mean()))
