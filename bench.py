@@ -655,6 +655,32 @@ def run_dropin(ctx, mode, rows=500_000):
     return out
 
 
+def run_train_step(ctx, batch=4096):
+    """Training step of the differentiable path (agent.py:60-87: NLL of a batch, loss.backward(), optimiser step): symsol.yml
+    (F = 512), one feature row per rotation as in training.  Reported next to the inference figures; not BASELINE's metric."""
+    from oracle import rnf_oracle as orc
+    cfg, flow = build_flow("symsol")
+    flow = flow.to(ctx.dev).train()
+    gen = torch.Generator().manual_seed(12)
+    R = orc.random_rotations(batch, gen).to(ctx.dev)
+    feat = torch.relu(torch.randn(batch, 512, generator=gen)).to(ctx.dev)
+    opt = torch.optim.Adam(flow.parameters(), lr=1e-4)
+    losses = []
+
+    def step():
+        _, ldj = flow(R, feat)
+        loss = -ldj.mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        losses.append(loss.detach())
+
+    ms = ctx.timed(step, 5, 3)
+    return {"rotations_per_s": batch / (ms * 1e-3), "ms_per_step": ms, "batch": batch,
+            "loss_first_last": [float(losses[0]), float(losses[-1])],
+            "config": "symsol.yml (F=512, 42 layers), forward + backward + Adam step through rotationnormflow_b200.train (conditioner MLP: cuBLAS FP32; Mobius mixture / calculate_16 forward + VJP: csrc/train_ops.cu)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -703,6 +729,10 @@ def main():
         r5, _ = run_grid_config(ctx, 5, mode, 2, 3, want_e2e=False)
         extra["5"] = {k: r5[k] for k in ("metric", "value", "ms_per_step", "config", "roofline")}
         line["e2e_dropin"] = run_dropin(ctx, mode)
+        try:
+            line["train_step"] = run_train_step(ctx)
+        except Exception as e:  # an extra leg: never fail the bench line over it
+            line["train_step"] = {"error": repr(e)[:200]}
         extra["5"]["note"] = "one GPU scoring the whole 37.7 M grid: the N = 1 point of the strong-scaling series the default run measures under torchrun"
         line["configs"] = extra
     if ctx.rank == 0 and ctx.world == 1 and cfg_id == 2 and not args.no_cpu_baseline:

@@ -159,7 +159,40 @@ __device__ __forceinline__ void relu_split_pair(float x0, float x1, uint32_t& hi
 
 // Epilogue of one GEMM: my row of the accumulator -> (+ c) -> ReLU -> fp16 hi / lo -> A operand in TMEM (K element 2e in the
 // low half of column e).  The four stores are waited for once.
+#ifndef RNF_T4_EPI_ASYNC
+#define RNF_T4_EPI_ASYNC 1       // all four 16-column loads of the accumulator in flight before the first wait (+1 %, fewer spills)
+#endif
 __device__ __forceinline__ void epilogue64(uint32_t tm, const float* cadd) {
+#if RNF_T4_EPI_ASYNC
+  float a0[16], a1[16], a2[16], a3[16];
+  tmem_ld16_async(tm + kColD, a0);
+  tmem_ld16_async(tm + kColD + 16, a1);
+  tmem_ld16_async(tm + kColD + 32, a2);
+  tmem_ld16_async(tm + kColD + 48, a3);
+  tmem_ld_wait16(a0); tmem_ld_wait16(a1); tmem_ld_wait16(a2); tmem_ld_wait16(a3);
+  float* q[4] = {a0, a1, a2, a3};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      float* acc = q[2 * h + g];
+      if (cadd != nullptr) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 c = __ldg(reinterpret_cast<const float4*>(cadd + 32 * h + 16 * g) + j4);
+          acc[4 * j4] += c.x; acc[4 * j4 + 1] += c.y; acc[4 * j4 + 2] += c.z; acc[4 * j4 + 3] += c.w;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) relu_split_pair(acc[2 * e], acc[2 * e + 1], hi[8 * g + e], lo[8 * g + e]);
+    }
+    tmem_st16_nowait(tm + kColAhi + 16 * h, hi);
+    tmem_st16_nowait(tm + kColAlo + 16 * h, lo);
+  }
+  tmem_st_wait();
+  return;
+#endif
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float acc[32];
