@@ -119,6 +119,11 @@ def small_cases():
     flow_case("s_mobonly", "raw", 11, 128, 0, True, layers=2, rot="None")
 
 
+def clu_cases():
+    """Condition16TransLU (flow/squeezetrans.py:94-144): batch-coupled in the reference; golden = what the reference computes."""
+    flow_case("s_clu", "modelnet_uni", 23, 64, 2, True, layers=2, lu=1, feature_dim=8, embedding=0)
+
+
 def ablation_cases():
     """Ablation replacements of the affine layer (flow/affineflow.py:27-41,55-70), unconditional and conditional."""
     flow_case("s_smith9", "raw", 12, 128, 0, True, layers=2, rot="9TransLSmith")
@@ -142,7 +147,7 @@ def full_cases():
     flow_case("modelnet", "modelnet_fisher", 0, 256, 4, False, with_fisher=True)
 
 
-GROUPS = {"small": small_cases, "ablation": ablation_cases, "full": full_cases, "grid": grid_case}
+GROUPS = {"small": small_cases, "clu": clu_cases, "ablation": ablation_cases, "full": full_cases, "grid": grid_case}
 
 
 def main():

@@ -313,6 +313,13 @@ def affine_matrix(sd, prefix, kind, feature, inverse):
         W = lu_weight(sd, prefix + "mat.")
     elif kind == "aff_c":
         W = conditioner(sd, prefix + "net.", feature).reshape(-1, 4, 4) + eye
+    elif kind == "aff_clu":
+        # ConditionLU.forward as written (flow/squeezetrans.py:121-128): torch.diag of the [N,4] tensor is the batch's diagonal
+        g = lambda n: sd[prefix + "net." + n]
+        low = conditioner(sd, prefix + "net.w_l_net.", feature).reshape(-1, 4, 4) * g("l_mask") + g("l_eye")
+        up = conditioner(sd, prefix + "net.w_u_net.", feature).reshape(-1, 4, 4) * g("u_mask") + torch.diag(
+            g("s_sign") * torch.exp(conditioner(sd, prefix + "net.w_s_net.", feature)))
+        W = torch.einsum("ab,nbc,ncd->nad", g("w_p"), low, up)
     elif kind == "rot_u":
         W = rot_weight(sd[prefix + "rot"])
         return (W.transpose(-1, -2) if inverse else W), False
@@ -430,7 +437,7 @@ class OracleFlow:
         self.K = cfg.segments
         self.plan = layer_plan(cfg)
         for k in self.plan:
-            if k is None or str(k).startswith("unsupported") or k == "aff_clu":
+            if k is None or str(k).startswith("unsupported"):
                 raise NotImplementedError(f"layer kind {k!r} is outside the hot-path scope (SURVEY.md section 2 rows 5,7)")
         self.sd = {k: torch.as_tensor(v).detach().to(self.device).to(dtype if torch.as_tensor(v).is_floating_point() else torch.as_tensor(v).dtype)
                    for k, v in state_dict.items()}

@@ -281,6 +281,9 @@ def layer_tensors(layer) -> list:
     if layer.kind == "aff_lu" or (layer.kind.endswith("_u") and isinstance(getattr(layer, "mat", None), torch.nn.Module)):
         m = layer.mat
         return [m.w_p, m.u_mask, m.l_mask, m.s_sign, m.l_eye, m.w_l, m.w_s, m.w_u]
+    if layer.kind == "aff_clu":
+        n = layer.net
+        return [t for ct in (n.w_l_net, n.w_u_net, n.w_s_net) for t in conditioner_tensors(ct).values()]
     if layer.kind.split("_")[0] in ABLATION_KINDS:
         return list(conditioner_tensors(layer.net).values()) if layer.kind.endswith("_c") else [layer.mat]
     return [t for t in list(layer.parameters()) + list(layer.buffers())]

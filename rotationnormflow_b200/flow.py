@@ -174,6 +174,53 @@ class Uncondition16TransLU(_FusedLayer):
             return self.mat()
 
 
+class ConditionLU(nn.Module):
+    """flow/squeezetrans.py:94-129: the feature-conditioned PLU parameterisation, reproduced as written.  NOTE the reference applies
+    ``torch.diag`` to the [N,n] output of ``w_s_net``: that returns the DIAGONAL of the batch (entry j of row j, j < n) and broadcasts
+    it over the columns of every row's U factor -- the layer is batch-coupled (rows 0..n-1 of the feature batch decide ``d`` for all
+    rows).  With the reference's own calling convention (one image's feature repeated, eval.py:450) it is well defined per image."""
+
+    def __init__(self, in_channel: int, feature_dim: int):
+        super().__init__()
+        from scipy import linalg as la
+        self.in_channel = in_channel
+        q, _ = la.qr(np.random.randn(in_channel, in_channel))
+        p, l, u = la.lu(q.astype(np.float32))
+        s = np.diag(u)
+        um = np.triu(np.ones_like(np.triu(u, 1)), 1)
+        self.register_buffer("w_p", torch.from_numpy(p))
+        self.register_buffer("u_mask", torch.from_numpy(um))
+        self.register_buffer("l_mask", torch.from_numpy(um.T.copy()))
+        self.register_buffer("s_sign", torch.sign(torch.from_numpy(np.copy(s))))
+        self.register_buffer("l_eye", torch.eye(in_channel))
+        self.w_l_net = ConditionalTransform(feature_dim, in_channel * in_channel)
+        self.w_u_net = ConditionalTransform(feature_dim, in_channel * in_channel)
+        self.w_s_net = ConditionalTransform(feature_dim, in_channel)
+
+    def weight(self, feature):
+        """[N,n,n], the expression of flow/squeezetrans.py:121-128 (library GEMMs on the feature rows; differentiable)."""
+        n = self.in_channel
+        low = engine.conditioner_torch(self.w_l_net, feature).reshape(-1, n, n) * self.l_mask + self.l_eye
+        up = engine.conditioner_torch(self.w_u_net, feature).reshape(-1, n, n) * self.u_mask \
+            + torch.diag(self.s_sign * torch.exp(engine.conditioner_torch(self.w_s_net, feature)))
+        return torch.einsum("ab,nbc,ncd->nad", self.w_p, low, up)
+
+
+class Condition16TransLU(_FusedLayer):
+    """flow/squeezetrans.py:132-144.  Batch-coupled (see ConditionLU): always evaluated by the per-layer operators of train.py."""
+
+    kind = "aff_clu"
+    uses_feature = True
+
+    def __init__(self, feature_dim):
+        super().__init__()
+        self.feature_dim = feature_dim
+        self.net = ConditionLU(4, feature_dim)
+
+    def _feature_dim(self):
+        return self.feature_dim
+
+
 class Condition16Trans(_FusedLayer):
     """flow/squeezetrans.py:41-55: W = MLP(feature).reshape(4,4) + I, evaluated once per image on device."""
 
@@ -325,10 +372,11 @@ def get_affine(config, feature_dim, first_layer_condition=False):
     rot, lu = config.rot, bool(getattr(config, "lu", 0))
 
     def lu_conditional(n):
+        if n == 4:
+            return Condition16TransLU(feature_dim)
         raise NotImplementedError(
-            f"Condition{n * n}TransLU (flow/squeezetrans.py:94-144,265-277) is batch-coupled in the reference (ConditionLU applies "
-            "torch.diag to a [N,n] tensor, which returns a diagonal instead of building one per row); there is no well-defined "
-            "per-rotation function to reproduce")
+            "Condition9TransLU (flow/squeezetrans.py:265-277): calculate_9 with the batch-coupled ConditionLU(3) has no per-image "
+            "parameter block for the fused kernels and no differentiable operator here")
 
     if first_layer_condition:
         if rot == "16UnTrans":
@@ -419,10 +467,9 @@ def _wants_grad(layers, rotation, feature) -> bool:
 
 
 _GRAD_MESSAGE = (
-    "rotationnormflow_b200 evaluates the flow in fused, non-differentiable CUDA kernels; this call runs with autograd enabled "
-    "and {what} requires grad, so the reference would build a graph here (flow/flow.py:53-92, training at agent.py:87, "
-    "eval.py:468-477).  Wrap inference in torch.no_grad() (as eval.py:539 / agent.py:102 do); returning detached outputs "
-    "silently would make backward() a no-op for the flow.")
+    "Flow.grid_log_prob is the fused grid evaluation (arg-max / normaliser reduced on the fly) and keeps nothing for a backward pass; "
+    "this call runs with autograd enabled and {what} requires grad.  Wrap it in torch.no_grad() (as eval.py:539 / agent.py:102 do), or "
+    "call Flow.forward / Flow.inverse, which run the differentiable per-layer operators (rotationnormflow_b200/train.py) in that case.")
 
 
 def _check_rotation(rotation):
@@ -437,7 +484,7 @@ def _needs_composed(layers, rotation, feature) -> bool:
     """True when the call must run layer by layer in the differentiable operators of train.py: autograd is on and something
     requires grad (the reference builds a graph there: training at agent.py:87, eval.py:468-477), or a Mobius layer has a number of
     mixture components other than the 64 the fused kernels are specialised for."""
-    if any(l.kind == "mobius" and l.K != engine.K_SEGMENTS for l in layers):
+    if any((l.kind == "mobius" and l.K != engine.K_SEGMENTS) or l.kind == "aff_clu" for l in layers):
         return True
     return _wants_grad(layers, rotation, feature)
 
@@ -569,6 +616,9 @@ class Flow(_NoProgramState, nn.Module):
         G_ = _check_rotation(grid)
         if torch.is_grad_enabled() and torch.is_tensor(feature) and feature.requires_grad:
             raise NotImplementedError(_GRAD_MESSAGE.format(what="the feature"))
+        if any((l.kind == "mobius" and l.K != engine.K_SEGMENTS) or l.kind == "aff_clu" for l in self.layers):
+            raise NotImplementedError(f"Flow.grid_log_prob runs in the fused kernels, which are specialised for segments={engine.K_SEGMENTS} and "
+                                      "per-image conditional affines; use Flow.forward on the grid rotations for other segment counts / ConditionLU")
         prog = _program(self, list(self.layers), self._perm_rows(), self.feature_dim, G_.device)
         cond, B = None, 1
         if prog.cond_floats:

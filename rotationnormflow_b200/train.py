@@ -98,6 +98,8 @@ def _affine_matrix(layer, rows, inverse: bool):
     elif kind in ("aff_c", "rot_c"):
         eye = torch.eye(4, device=rows.device, dtype=rows.dtype)
         W = engine.conditioner_torch(layer.net, rows).reshape(-1, 4, 4) + eye
+    elif kind == "aff_clu":
+        W = layer.net.weight(rows)                            # batch-coupled in the reference; reproduced as written
     elif kind == "rot_u":
         W = layer.rot
     else:

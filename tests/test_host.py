@@ -45,11 +45,10 @@ def test_layer_stack_matches_oracle_plan():
 
 
 def test_out_of_scope_layers_raise():
-    # ConditionLU (Condition16TransLU / Condition9TransLU) is batch-coupled in the reference: torch.diag of a [N,n] tensor
-    with pytest.raises(NotImplementedError):
-        rnf.get_flow(rnf.load_config("modelnet_uni", lu=1))
+    # Condition9TransLU: calculate_9 with the batch-coupled ConditionLU(3) (torch.diag of a [N,3] tensor) is the one layer left out
     with pytest.raises(NotImplementedError):
         rnf.get_flow(rnf.load_config("modelnet_uni", rot="9TransLSmith", lu=1))
+    assert rnf.get_flow(rnf.load_config("modelnet_uni", lu=1, layers=1)).layers[1].kind == "aff_clu"
     # config.segments != 64 is accepted (it runs in the per-layer operators of train.py, tests/test_gpu_train.py)
     assert rnf.get_flow(rnf.load_config("raw", segments=32, layers=1)).layers[0].K == 32
 
