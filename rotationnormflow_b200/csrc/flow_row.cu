@@ -36,6 +36,9 @@ namespace {
 #ifndef RNF_INV_NEWTON
 #define RNF_INV_NEWTON 1         // inverse: locate the root with Newton steps, then replay the reference's 15 halvings (see below)
 #endif
+#ifndef RNF_INV_DELTA
+#define RNF_INV_DELTA 1          // inverse: theta_k = t + 2 asin(sin delta_k) (no quadrant logic), see mobius_pair.cuh probe_delta_pairs
+#endif
 constexpr int kThreads = 256;
 constexpr int kRows = 128;                        // rows per tile = TMEM lanes = threads per tile
 
@@ -383,14 +386,26 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
 #pragma unroll 1
           for (int j = 0; j < 4; ++j) {
             tmem_ld32_async(tm + 64 * j + 32, bufB);
+#if RNF_INV_DELTA
+            probe_delta_pairs<4, RNF_INV_NEWTON != 0>(cs, sn, bufA, Fs2, Sf2);
+#else
             probe_pairs<4, RNF_INV_NEWTON != 0>(cs, sn, bufA, Fs2, &Sf2);
+#endif
             tmem_ld_wait32(bufB);
             if (j < 3) tmem_ld32_async(tm + 64 * j + 64, bufA);
+#if RNF_INV_DELTA
+            probe_delta_pairs<4, RNF_INV_NEWTON != 0>(cs, sn, bufB, Fs2, Sf2);
+#else
             probe_pairs<4, RNF_INV_NEWTON != 0>(cs, sn, bufB, Fs2, &Sf2);
+#endif
             if (j < 3) tmem_ld_wait32(bufA);
           }
           dF = hsum(Sf2) / S_sp;
+#if RNF_INV_DELTA
+          return fmaf(2.0f, hsum(Fs2) / S_sp, t) - ys;  // sum_k pi_k theta_k = t + 2 sum_k pi_k delta_k
+#else
           return hsum(Fs2) / S_sp - ys;                // the reference's f(x0), same arithmetic for every use
+#endif
         };
         float lo = kPi / 2.0f, hi = 1.5f * kPi, x0 = 0.0f;
         int n_eval = 0;                               // evaluations of F by this warp in this layer (measurement hook)

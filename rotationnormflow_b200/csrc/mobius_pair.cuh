@@ -248,6 +248,32 @@ __device__ __forceinline__ void probe_pairs(float zr, float zv, const float* prm
   }
 }
 
+// The same evaluation without any quadrant logic.  On the unit circle the Mobius map is the disk automorphism
+// h = (z - w') / (1 - conj(w') z), so  theta_k = arg h = 2 arg(z - w') - t  with z = e^{it}; and because |w'| < 0.7 the direction of
+// z - w' deviates from the direction of z by  delta_k = asin( (z x (z - w')) / |z - w'| ),  |sin delta_k| <= 0.7:
+//     theta_k = t + 2 delta_k,      sum_k weight_k theta_k = t sum_k weight_k + 2 sum_k weight_k delta_k
+// -- one rsqrt gives both sin(delta) and f = (1 - |w'|^2) / |z - w'|^2, the asin polynomial needs no min / max / select / copysign,
+// and for t in [pi/2, 3pi/2] the result lies in (0.02, 6.27): already wrapped.  Accumulates Ds += weight delta (and Sf += weight f).
+template <int NP, bool DERIV>
+__device__ __forceinline__ void probe_delta_pairs(float zr, float zv, const float* prm, f32x2& Ds, f32x2& Sf) {
+  f32x2 m[NP], ms[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const f32x2 nal = pk(prm[8 * j], prm[8 * j + 1]), nbe = pk(prm[8 * j + 2], prm[8 * j + 3]);
+    const f32x2 dr = add2(nal, bc(zr)), dv = add2(nbe, bc(zv));          // z - w'
+    const f32x2 dd = fma2(dv, dv, mul2(dr, dr));
+    const f32x2 cr = fma2(dr, bc(-zv), mul2(dv, bc(zr)));                // z x (z - w') = cos t dv - sin t dr
+    f32x2 rs;
+    RNF_MAP2(rs, dd, rsqrt_approx);
+    const f32x2 rs2 = mul2(rs, rs);
+    m[j] = mul2(cr, rs);
+    ms[j] = mul2(mul2(cr, cr), rs2);
+    if (DERIV) Sf = fma2(pk(prm[8 * j + 6], prm[8 * j + 7]), mul2(pk(prm[8 * j + 4], prm[8 * j + 5]), rs2), Sf);
+  }
+#pragma unroll
+  for (int j = 0; j < NP; ++j) Ds = fma2(pk(prm[8 * j + 6], prm[8 * j + 7]), asin_unit2_s(m[j], ms[j]), Ds);
+}
+
 // sum_k weight_k f_k(z) over NP prepared pairs (log-det of the inverse direction, flow/mobiusflow.py:169-181)
 template <int NP>
 __device__ __forceinline__ void jacobian_pairs(float zr, float zv, const float* prm, f32x2& Sf) {
