@@ -17,6 +17,8 @@
 //     block (c_hi, c_lo) in grid mode (a tile never straddles images); in row mode it is added in the epilogue.
 // One thread owns one rotation (512 threads = 4 tiles x 128 rows): nothing is computed twice, nothing is exchanged.
 // The bisection of Flow.inverse needs its 256 prepared parameters resident per row and stays in flow_row.cu.
+#include <cstdlib>
+
 #include "mobius_pair.cuh"
 #include "tc_common.cuh"
 #include "ablation_layers.cuh"
@@ -261,8 +263,12 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
   const uint32_t tm_tile = tmem_base + (uint32_t)tile * kColsPerTile;                   // lane 0 of the tile (MMA addresses)
   const uint32_t tm = tm_tile + ((uint32_t)((warp & 3) * 32) << 16);                    // my warp's lane quarter
 
-  const int64_t n_groups = (a.n_tiles + kTiles - 1) / kTiles;
-  const int64_t my_items = blockIdx.x < n_groups ? (n_groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  // Tiles in flight in this launch (launch_flow_t4): 4 for large launches; a launch of only a few tiles per SM balances better with
+  // fewer (e.g. 5.3 tiles per SM as 2 rounds of 3 instead of a round of 4 and a round of 4 on a third of the SMs).  The warps of
+  // the unused tile slots skip the work loop.
+  const int n_active = a.t4_active > 0 && a.t4_active < kTiles ? a.t4_active : kTiles;
+  const int64_t n_groups = (a.n_tiles + n_active - 1) / n_active;
+  const int64_t my_items = (blockIdx.x < n_groups && tile < n_active) ? (n_groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
   const int64_t total_steps = my_items * n_mob;
   const uint8_t* wbytes = reinterpret_cast<const uint8_t*>(a.weights);
   // piece 0..2 = W1..W3, 3 = W4, 4 = aux (into buffer abuf): one bulk copy each, signalled on the piece's mbarrier.
@@ -329,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
   };
 
   for (int64_t item = 0; item < my_items; ++item) {
-    const int64_t tile_idx = kTiles * (blockIdx.x + item * (int64_t)gridDim.x) + tile;
+    const int64_t tile_idx = n_active * (blockIdx.x + item * (int64_t)gridDim.x) + tile;
     int64_t row = 0, img = 0, g = 0;
     bool valid = false;
     float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
@@ -461,8 +467,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
         TRACE(3 + 3 * l);
         // a piece is dead once ALL tiles' GEMM that reads it has completed: the last tile to get here refills it
         if (elected) {
-          if (l == 0) { if ((atomicAdd(&s_cnt[4 + abuf], 1) % kTiles) == kTiles - 1 && step + 2 < total_steps) load_piece(mob_n2, 4, abuf); }
-          else if ((atomicAdd(&s_cnt[l - 1], 1) % kTiles) == kTiles - 1 && step + 1 < total_steps) load_piece(mob_n1, l - 1, 0);
+          if (l == 0) { if ((atomicAdd(&s_cnt[4 + abuf], 1) % n_active) == n_active - 1 && step + 2 < total_steps) load_piece(mob_n2, 4, abuf); }
+          else if ((atomicAdd(&s_cnt[l - 1], 1) % n_active) == n_active - 1 && step + 1 < total_steps) load_piece(mob_n1, l - 1, 0);
         }
         const float* ca = (l == 0 || l == 3) ? cadd : nullptr;
         epilogue64(tm, ca);
@@ -496,7 +502,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
       // W4 is dead the moment the last chunk's MMAs have completed (not after the arithmetic on it): the last tile to see that
       // refills it.  (Refilling W4 chunk by chunk removes the leaders' remaining wait for it but lets three tiles fall into
       // lock step: 222 M instead of 238 M rot/s -- the coupling through this one piece keeps the tiles in two anti-phase pairs.)
-#define W4_DONE() do { if (c == 3 && elected && (atomicAdd(&s_cnt[3], 1) % kTiles) == kTiles - 1 && step + 1 < total_steps) load_piece(mob_n1, 3, 0); } while (0)
+#define W4_DONE() do { if (c == 3 && elected && (atomicAdd(&s_cnt[3], 1) % n_active) == n_active - 1 && step + 1 < total_steps) load_piece(mob_n1, 3, 0); } while (0)
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
 #if RNF_T4_NP == 4
@@ -630,13 +636,36 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
 
 }  // namespace
 
-cudaError_t launch_flow_t4(const FlowArgs& a, int sm_count, cudaStream_t st) {
+// Tiles in flight per CTA for a launch of n_tiles over sm_count persistent CTAs: minimise rounds x (relative duration of a round
+// with a tiles in flight).  Round durations measured with the RNF_T4_ACTIVE override on raw.yml, eight full rounds each
+// (tools/active_tiles_probe.py, profiles/r02_active_tiles.txt): 88 / 154 / 182 / 225 M rot/s with 1 / 2 / 3 / 4 tiles in flight,
+// i.e. a round of one tile lasts 0.64 of a round of four, two 0.73, three 0.93.
+static int pick_active_tiles(int64_t n_tiles, int sm_count) {
+  static const float kRound[5] = {0.f, 0.637f, 0.731f, 0.926f, 1.0f};
+  int best = kTiles;
+  float best_cost = 1e30f;
+  for (int act = kTiles; act >= 1; --act) {
+    const int64_t groups = (n_tiles + act - 1) / act;
+    const int64_t rounds = (groups + sm_count - 1) / sm_count;
+    const float cost = (float)rounds * kRound[act];
+    if (cost < best_cost - 1e-6f) { best_cost = cost; best = act; }
+  }
+  return best;
+}
+
+cudaError_t launch_flow_t4(const FlowArgs& a_in, int sm_count, cudaStream_t st) {
+  FlowArgs a = a_in;
   const bool grid_mode = a.G > 0;
   void (*kern)(const FlowArgs) = grid_mode ? flow_t4_kernel<true> : flow_t4_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc);
   if (e != cudaSuccess) return e;
   if (a.n_tiles <= 0) return cudaSuccess;
-  const int64_t groups = (a.n_tiles + kTiles - 1) / kTiles;
+  a.t4_active = kTiles == 4 ? pick_active_tiles(a.n_tiles, sm_count) : kTiles;
+  if (const char* force = getenv("RNF_T4_ACTIVE")) {         // measurement override (tools/): tiles in flight, 1..4
+    const int v = atoi(force);
+    if (v >= 1 && v <= kTiles) a.t4_active = v;
+  }
+  const int64_t groups = (a.n_tiles + a.t4_active - 1) / a.t4_active;
   const int64_t grid = groups < sm_count ? groups : sm_count;
   kern<<<(unsigned)grid, kThreads, kSmemAlloc, st>>>(a);
   return cudaGetLastError();

@@ -68,6 +68,7 @@ struct FlowArgs {
   float* part;        // [n_tiles][kPartStride]: (max, sum exp(lp - max), argmax lo, argmax hi, sum exp(lp - max) * d_gt, -, -, -)
   const float* gt;    // [B][gt_k][9] ground-truth rotations per image (spread metric), nullptr = not requested
   int gt_k;
+  int t4_active;      // flow_t4: tiles in flight per CTA in this launch (set by launch_flow_t4; 0 = all four)
   unsigned long long* probe_counter;   // measurement hook (rnf_debug_set_probe_counter), normally null
   long long* trace;   // debug builds (-DRNF_TC_TRACE): per-phase clock64() stamps of CTA 0, else unused
 };
