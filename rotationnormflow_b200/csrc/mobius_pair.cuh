@@ -186,10 +186,12 @@ __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv
   } else {
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-      f32x2 rc;
-      RNF_MAP2(rc, u[j], rcp_approx);
-      const f32x2 nal = mul2(neg2(ap[j]), rc), nbe = mul2(neg2(bp[j]), rc);
-      const f32x2 omw = fma2(neg2(mul2(rc, rc)), n2[j], bc(1.0f));      // 1 - |w'|^2
+      // -1 / u from the reciprocal of -u (a packed sign flip costs two LOP3: ncu r02, 4 % of the inverse kernel's instructions)
+      const f32x2 nu = fma2(rt[j], bc(-1.4285714285714286f), bc(-1.0f));
+      f32x2 nrc;
+      RNF_MAP2(nrc, nu, rcp_approx);
+      const f32x2 nal = mul2(ap[j], nrc), nbe = mul2(bp[j], nrc);
+      const f32x2 omw = fma2(fma2(nal, nal, mul2(nbe, nbe)), bc(-1.0f), bc(1.0f));      // 1 - |w'|^2
       S_sp = add2(S_sp, sp[j]);
       upk(nal, raw[8 * j], raw[8 * j + 1]);
       upk(nbe, raw[8 * j + 2], raw[8 * j + 3]);
