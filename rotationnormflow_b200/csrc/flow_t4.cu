@@ -15,7 +15,14 @@
 //     bias, W0.y (error-compensated) and, in the last hidden layer, x0 again -- no stash of x0, no FMA loop on the CUDA cores.
 //     The per-image term  c = W_f.feature  (hoisted, rnf_flow_condition) enters through one more K = 16 MMA against a per-tile
 //     block (c_hi, c_lo) in grid mode (a tile never straddles images); in row mode it is added in the epilogue.
-// One thread owns one rotation (512 threads = 4 tiles x 128 rows): nothing is computed twice, nothing is exchanged.
+// One WORKER thread owns one rotation (512 threads = 4 tiles x 128 rows): nothing is computed twice, nothing is exchanged.
+//
+// Warp specialisation (round 2): a fifth warpgroup holds one SERVICE warp per tile that does nothing but wait for the tile's
+// hand-over (an mbarrier the four worker warps arrive on), issue the tile's MMAs, wake the workers when a dependent GEMM has
+// completed, and refill weight pieces.  Before, one of the tile's own worker warps issued: tcgen05.mma issue blocks at the pace
+// of the tensor pipe (13 MMAs = ~450 cycles per GEMM, eight GEMMs per layer), so that warp ran ~30 % behind its three siblings
+// and every hand-over of the tile waited for it.  Registers: 640 threads launch with 96 each (the CTA's pool); the service warpgroup
+// drops to 32 (setmaxnreg.dec) and the four worker warpgroups take 112 (setmaxnreg.inc): 512 x 112 + 128 x 32 = 640 x 96.
 // The bisection of Flow.inverse needs its 256 prepared parameters resident per row and stays in flow_row.cu.
 #include <cstdlib>
 
@@ -35,34 +42,21 @@ namespace {
 #define TRACE(i) do { } while (0)
 #endif
 
-#ifndef RNF_T4_TILES
-#define RNF_T4_TILES 4           // tiles in flight per SM (4 = TMEM and register-file ceiling at 128 registers per thread)
-#endif
-#ifndef RNF_T4_FHFMA
-#define RNF_T4_FHFMA 0
-#endif
-#ifndef RNF_T4_ROTATE_ISSUER
-#define RNF_T4_ROTATE_ISSUER 1
-#endif
 #ifndef RNF_T4_SPLIT_MASK
 #define RNF_T4_SPLIT_MASK 1
 #endif
-#ifndef RNF_T4_EARLY_W
-#define RNF_T4_EARLY_W 1         // look at the next GEMM's weight barrier right after issuing the current one
+#ifndef RNF_T4_WORKER_REGS
+#define RNF_T4_WORKER_REGS 112
 #endif
-#ifndef RNF_T4_WAIT_BAR
-#define RNF_T4_WAIT_BAR 1        // long waits: one polling warp per tile, the others in a named barrier
+#ifndef RNF_T4_SERVICE_REGS
+#define RNF_T4_SERVICE_REGS 32
 #endif
-#ifndef RNF_T4_NP
-#define RNF_T4_NP 2              // mixture pairs evaluated together
-#endif
-#ifndef RNF_T4_YIELD
-#define RNF_T4_YIELD 0           // experiment: scheduler yields inside the mixture (1 = once per chunk, 2 = after every block of pairs)
-#endif
-#define T4_YIELD(level) do { if (RNF_T4_YIELD >= (level)) __nanosleep(0); } while (0)
-constexpr int kTiles = RNF_T4_TILES;
-constexpr int kThreads = kTiles * 128;
+constexpr int kTiles = 4;            // tiles in flight per SM (TMEM: 4 x 128 columns)
+constexpr int kWorkers = kTiles * 128;
+constexpr int kThreads = kWorkers + kTiles * 32;   // + one service warp per tile (warpgroup 4)
 constexpr int kRows = 128;
+// setmaxnreg moves registers inside the pool the CTA was LAUNCHED with (640 threads x 96, the largest multiple of 8 that fits the file)
+static_assert(kWorkers * RNF_T4_WORKER_REGS + kTiles * 32 * RNF_T4_SERVICE_REGS <= kThreads * 96, "register pool of the CTA");
 
 // shared memory (bytes from a 1024-aligned base)
 constexpr int kOffW = 0;                                  // W1 | W2 | W3 pieces
@@ -78,7 +72,9 @@ constexpr int kSmemAlloc = kSmemBytes + 1024;
 static_assert(kOffLastW % 1024 == 0 && kW1Bytes % 1024 == 0, "UMMA SW128 tiles need 1024 B alignment");
 static_assert(kOffY % 16 == 0 && kOffC % 16 == 0 && kOffAux % 16 == 0, "no-swizzle blocks need 16 B alignment");
 
-enum { BAR_W_FULL = 0 /* W1,W2,W3,W4 */, BAR_AUX_FULL = 4 /* [2] */, BAR_MMA = 6 /* [tile] */, BAR_COUNT = 6 + RNF_T4_TILES };
+enum { BAR_W_FULL = 0 /* W1,W2,W3,W4 */, BAR_AUX_FULL = 4 /* [2] */, BAR_MMA = 6 /* [tile] */, BAR_READY = 6 + kTiles /* [tile] */,
+       BAR_COUNT = 6 + 2 * kTiles };
+static_assert(BAR_COUNT <= 16, "mbarrier slots");
 
 // TMEM columns of a tile
 constexpr uint32_t kColAhi = 0, kColAlo = 32, kColD = 64, kColsPerTile = 128;
@@ -114,24 +110,15 @@ __device__ __forceinline__ uint32_t pack_h2(__half lo, __half hi) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // ReLU + error-compensated fp16 split of two activations (tc_common.cuh: relu_split2) with the residual taken packed.
 // (The mixed-precision FHFMA form of the residual, fma.rn.f32.f16, issues one instruction less but runs at a quarter of the
 // FMA rate: tools/cvt_rate.cu.)
 __device__ __forceinline__ void relu_split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-#if RNF_T4_FHFMA
-  asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
-  float d0, d1;
-  asm("{\n"
-      ".reg .b16 h0, h1, m1;\n"
-      "mov.b32 {h0, h1}, %2;\n"
-      "mov.b16 m1, 0xBC00;\n"                       // -1.0 in fp16
-      "fma.rn.f32.f16 %0, h0, m1, %3;\n"
-      "fma.rn.f32.f16 %1, h1, m1, %4;\n"
-      "}\n"
-      : "=f"(d0), "=f"(d1)
-      : "r"(hi), "f"(x0), "f"(x1));
-  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
-#elif RNF_T4_SPLIT_MASK == 2
+#if RNF_T4_SPLIT_MASK == 2
   // mixed: one value by the mask (ALU pipe), the other by the conversion (FMA pipe) -- ncu r02: ALU 40 %, FMA 23 % with both on the ALU
   asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
   const float m0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
@@ -160,12 +147,8 @@ __device__ __forceinline__ void relu_split_pair(float x0, float x1, uint32_t& hi
 }
 
 // Epilogue of one GEMM: my row of the accumulator -> (+ c) -> ReLU -> fp16 hi / lo -> A operand in TMEM (K element 2e in the
-// low half of column e).  The four stores are waited for once.
-#ifndef RNF_T4_EPI_ASYNC
-#define RNF_T4_EPI_ASYNC 1       // all four 16-column loads of the accumulator in flight before the first wait (+1 %, fewer spills)
-#endif
+// low half of column e).  All four 16-column loads are in flight before the first wait; the four stores are waited for once.
 __device__ __forceinline__ void epilogue64(uint32_t tm, const float* cadd) {
-#if RNF_T4_EPI_ASYNC
   float a0[16], a1[16], a2[16], a3[16];
   tmem_ld16_async(tm + kColD, a0);
   tmem_ld16_async(tm + kColD + 16, a1);
@@ -193,26 +176,134 @@ __device__ __forceinline__ void epilogue64(uint32_t tm, const float* cadd) {
     tmem_st16_nowait(tm + kColAlo + 16 * h, lo);
   }
   tmem_st_wait();
-  return;
-#endif
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    float acc[32];
-    tmem_ld32(tm + kColD + 32 * h, acc);
-    if (cadd != nullptr) {
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 c = __ldg(reinterpret_cast<const float4*>(cadd + 32 * h) + j4);
-        acc[4 * j4] += c.x; acc[4 * j4 + 1] += c.y; acc[4 * j4 + 2] += c.z; acc[4 * j4 + 3] += c.w;
-      }
-    }
-    uint32_t hi[16], lo[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) relu_split_pair(acc[2 * e], acc[2 * e + 1], hi[e], lo[e]);
-    tmem_st16_nowait(tm + kColAhi + 16 * h, hi);
-    tmem_st16_nowait(tm + kColAlo + 16 * h, lo);
+}
+
+template <int N>
+__device__ __forceinline__ void set_max_regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void set_max_regs_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+struct TileSched {            // which tiles / layer steps a tile slot of this CTA processes (same arithmetic in workers and service warp)
+  int n_active;
+  int my_items;               // < 2^31 / layers: a CTA's share of at most 2^31 tiles
+  int total_steps;
+};
+
+// ------------------------------------------------ service warp of one tile --------------------------------------------------
+// Mirrors the control flow of the tile's workers: per Mobius layer five hand-overs that end in a GEMM the workers WAIT for
+// (fc_first, three hidden layers, fc_last chunk 0) and three whose GEMM runs under the workers' arithmetic (chunks 1..3).
+template <bool GRID>
+__device__ __forceinline__ void service_warp(const FlowArgs& a, uint8_t* smem, const uint32_t tmem_base, const int tile, const int lane,
+                                             const TileSched sc, const int n_mob, const long long* s_moff, int* s_cnt) {
+  const uint32_t bars = smem_u32(smem + kOffBar);
+  const uint8_t* wbytes = reinterpret_cast<const uint8_t*>(a.weights);
+  // piece 0..2 = W1..W3, 3 = W4, 4 = aux (into buffer abuf): one bulk copy each, signalled on the piece's mbarrier.
+  // A piece is refilled for the next layer as soon as ALL tiles' MMAs that read it are done.
+  auto load_piece = [&](int mob_idx, int piece, int abuf) {
+    const uint8_t* src = wbytes + s_moff[mob_idx] * 4;
+    uint32_t dst, bytes, bar;
+    if (piece < 3) { src += piece * kW1Bytes; dst = kOffW + piece * kW1Bytes; bytes = kW1Bytes; bar = BAR_W_FULL + piece; }
+    else if (piece == 3) { src += kHidW; dst = kOffLastW; bytes = kLastW; bar = BAR_W_FULL + 3; }
+    else { src += kHidW + kLastW; dst = kOffAux + abuf * kAuxStride; bytes = kAuxBytes; bar = BAR_AUX_FULL + abuf; }
+    mbar_expect_tx(bars + 8 * bar, bytes);
+    bulk_g2s(smem_u32(smem + dst), src, bytes, bars + 8 * bar);
+  };
+  if (tile == 0 && lane == 0 && sc.total_steps > 0) {      // tile slot 0 is active whenever the CTA has work
+    for (int piece = 0; piece < 4; ++piece) load_piece(0, piece, 0);
+    load_piece(0, 4, 0);
+    if (sc.total_steps > 1) load_piece(n_mob > 1 ? 1 : 0, 4, 1);
   }
-  tmem_st_wait();
+  const uint32_t tm_tile = tmem_base + (uint32_t)tile * kColsPerTile;
+  const uint32_t y_d = umma_desc_lo_ns(smem_u32(smem + kOffY + tile * 4096)), c_d = umma_desc_lo_ns(smem_u32(smem + kOffC + tile * 2048));
+  const uint32_t w_hid_d = umma_desc_lo(smem_u32(smem + kOffW)), w_last_d = umma_desc_lo(smem_u32(smem + kOffLastW));
+  const uint32_t bias_hid_d = umma_desc_lo_ns(smem_u32(smem + kOffW + 16384)), bias_last_d = umma_desc_lo_ns(smem_u32(smem + kOffLastW + 65536));
+  const uint32_t aux_blk_d = umma_desc_lo_ns(smem_u32(smem + kOffAux + kAuxFirst));
+  const uint32_t bar_mma = bars + 8 * (BAR_MMA + tile), bar_ready = bars + 8 * (BAR_READY + tile);
+  const int bar_wait = 9 + tile;                     // named barrier the tile's workers sleep in during a GEMM round trip
+  constexpr uint32_t kIdesc = umma_idesc(128, 64);
+  const uint32_t d = tm_tile + kColD;
+  const int n_active = sc.n_active;
+  uint32_t par_mma = 0, par_ready = 0, par_w = 0;
+  int step = 0;
+  int mob_cur = 0;
+
+  auto wait_ready = [&]() {                          // the tile's four worker warps have handed over (Y block / A operand / drained D)
+    mbar_wait(bar_ready, par_ready);
+    par_ready ^= 1;
+    tc_fence_after();
+  };
+  auto wake_workers = [&]() {                        // the GEMM the workers sleep on has completed
+    mbar_wait(bar_mma, par_mma);
+    par_mma ^= 1;
+    tc_fence_before();
+    named_arrive(bar_wait, 128 + 32);
+  };
+
+  for (int item = 0; item < sc.my_items; ++item) {
+#pragma unroll 1
+    for (int li = 0; li < a.n_layers; ++li) {
+      const LayerDev L = a.layers[li];
+      if (L.kind != RNF_LAYER_MOBIUS) continue;
+      const bool c_by_mma = GRID && L.cond_slot >= 0 && a.cond != nullptr;
+      const int abuf = (int)(step & 1);
+      const int mob_n1 = mob_cur + 1 >= n_mob ? mob_cur + 1 - n_mob : mob_cur + 1;
+      const int mob_n2 = mob_n1 + 1 >= n_mob ? mob_n1 + 1 - n_mob : mob_n1 + 1;
+      // ---- fc_first and three hidden layers: four dependent GEMM round trips ----
+#pragma unroll 1
+      for (int l = 0; l < 4; ++l) {
+        if (l == 0) mbar_wait(bars + 8 * (BAR_AUX_FULL + abuf), (uint32_t)((step >> 1) & 1));
+        else mbar_wait(bars + 8 * (BAR_W_FULL + l - 1), (par_w >> (l - 1)) & 1u);
+        wait_ready();
+        if (elect_one_sync()) {
+          if (l == 0) {
+            umma_f16(d, y_d, aux_blk_d + abuf * (kAuxStride >> 4), kDescHiNS, kIdesc, 0);
+          } else {
+            const uint32_t wb = w_hid_d + (l - 1) * (kW1Bytes >> 4);
+            umma_f16(d, y_d, bias_hid_d + (l - 1) * (kW1Bytes >> 4), kDescHiNS, kIdesc, 0);
+            issue_split_ts(d, tm_tile + kColAhi, tm_tile + kColAlo, wb, wb + (8192 >> 4), kIdesc);
+          }
+          if (c_by_mma && (l == 0 || l == 3)) umma_f16(d, y_d, c_d, kDescHiNS, kIdesc, 1);
+          umma_commit(bar_mma);
+        }
+        __syncwarp();
+        wake_workers();
+        // a piece is dead once ALL tiles' GEMM that reads it has completed: the last tile to get here refills it
+        if (lane == 0) {
+          if (l == 0) { if ((atomicAdd(&s_cnt[4 + abuf], 1) % n_active) == n_active - 1 && step + 2 < sc.total_steps) load_piece(mob_n2, 4, abuf); }
+          else if ((atomicAdd(&s_cnt[l - 1], 1) % n_active) == n_active - 1 && step + 1 < sc.total_steps) load_piece(mob_n1, l - 1, 0);
+        }
+        __syncwarp();
+      }
+      // ---- fc_last in four N = 64 chunks through the single accumulator ----
+      mbar_wait(bars + 8 * (BAR_W_FULL + 3), (par_w >> 3) & 1u);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        wait_ready();                                // c == 0: last hidden epilogue done; c > 0: chunk c - 1 drained into registers
+        if (elect_one_sync()) {
+          const uint32_t wb = w_last_d + c * (8192 >> 4);                  // rows 64c .. 64c+63 of the hi plane
+          umma_f16(d, y_d, bias_last_d + c * (2048 >> 4), kDescHiNS, kIdesc, 0);
+          issue_split_ts(d, tm_tile + kColAhi, tm_tile + kColAlo, wb, wb + (32768 >> 4), kIdesc);
+          umma_commit(bar_mma);
+        }
+        __syncwarp();
+        if (c == 0) {
+          wake_workers();
+        } else if (c == 3) {
+          // W4 is dead the moment the last chunk's MMAs have completed (not after the arithmetic on it): the last tile to see
+          // that refills it.
+          mbar_wait(bar_mma, par_mma);
+          par_mma ^= 1;
+          if (lane == 0 && (atomicAdd(&s_cnt[3], 1) % n_active) == n_active - 1 && step + 1 < sc.total_steps) load_piece(mob_n1, 3, 0);
+          __syncwarp();
+        } else {
+          par_mma ^= 1;                              // chunks 1, 2: the workers poll the mbarrier themselves
+        }
+      }
+      par_w ^= 0xFu;
+      ++step;
+      mob_cur = mob_n1;
+    }
+  }
 }
 
 template <bool GRID>
@@ -221,17 +312,9 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int tile = warp >> 2;                        // 0..3
-  const int rowi = (warp & 3) * 32 + lane;           // row inside the tile = TMEM lane
-  // The warp that issues a tile's MMAs (and whose lane 0 counts / refills weight pieces) sits in a different lane quarter,
-  // i.e. on a different scheduler, for every tile: the ~1.2 k instructions of MMA issue per tile-layer are spread over the
-  // four schedulers instead of making scheduler 0's warps the ones every hand-over waits for.
-#if RNF_T4_ROTATE_ISSUER
-  const bool issuer_warp = (warp & 3) == (tile & 3);  // warp-uniform
-#else
-  const bool issuer_warp = (warp & 3) == 0;
-#endif
-  const bool elected = issuer_warp && lane == 0;
+  const bool service = warp >= kTiles * 4;           // warpgroup 4: one service warp per tile
+  const int tile = service ? warp - kTiles * 4 : warp >> 2;
+  const int rowi = (warp & 3) * 32 + lane;           // worker: row inside the tile = TMEM lane
   const uint32_t bars = smem_u32(smem + kOffBar);
 
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kOffMisc);
@@ -245,7 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
       ++n_mob;
     }
   if (tid == 0) {
-    for (int i = 0; i < BAR_COUNT; ++i) mbar_init(bars + 8 * i, 1);
+    for (int i = 0; i < BAR_COUNT; ++i) mbar_init(bars + 8 * i, (i >= BAR_READY) ? 4 : 1);   // ready: one arrival per worker warp
     for (int i = 0; i < 6; ++i) s_cnt[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -260,369 +343,252 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const uint32_t tm_tile = tmem_base + (uint32_t)tile * kColsPerTile;                   // lane 0 of the tile (MMA addresses)
-  const uint32_t tm = tm_tile + ((uint32_t)((warp & 3) * 32) << 16);                    // my warp's lane quarter
 
   // Tiles in flight in this launch (launch_flow_t4): 4 for large launches; a launch of only a few tiles per SM balances better with
   // fewer (e.g. 5.3 tiles per SM as 2 rounds of 3 instead of a round of 4 and a round of 4 on a third of the SMs).  The warps of
   // the unused tile slots skip the work loop.
-  const int n_active = a.t4_active > 0 && a.t4_active < kTiles ? a.t4_active : kTiles;
+  TileSched sc;
+  sc.n_active = a.t4_active > 0 && a.t4_active < kTiles ? a.t4_active : kTiles;
+  const int n_active = sc.n_active;
   const int64_t n_groups = (a.n_tiles + n_active - 1) / n_active;
-  const int64_t my_items = (blockIdx.x < n_groups && tile < n_active) ? (n_groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-  const int64_t total_steps = my_items * n_mob;
-  const uint8_t* wbytes = reinterpret_cast<const uint8_t*>(a.weights);
-  // piece 0..2 = W1..W3, 3 = W4, 4 = aux (into buffer abuf): one bulk copy each, signalled on the piece's mbarrier.
-  // A piece is refilled for the next layer as soon as ALL tiles' MMAs that read it are done.
-  auto load_piece = [&](int mob_idx, int piece, int abuf) {
-    const uint8_t* src = wbytes + s_moff[mob_idx] * 4;
-    uint32_t dst, bytes, bar;
-    if (piece < 3) { src += piece * kW1Bytes; dst = kOffW + piece * kW1Bytes; bytes = kW1Bytes; bar = BAR_W_FULL + piece; }
-    else if (piece == 3) { src += kHidW; dst = kOffLastW; bytes = kLastW; bar = BAR_W_FULL + 3; }
-    else { src += kHidW + kLastW; dst = kOffAux + abuf * kAuxStride; bytes = kAuxBytes; bar = BAR_AUX_FULL + abuf; }
-    mbar_expect_tx(bars + 8 * bar, bytes);
-    bulk_g2s(smem_u32(smem + dst), src, bytes, bars + 8 * bar);
-  };
-  if (tid == 0 && total_steps > 0) {
-    for (int piece = 0; piece < 4; ++piece) load_piece(0, piece, 0);
-    load_piece(0, 4, 0);
-    if (total_steps > 1) load_piece(n_mob > 1 ? 1 : 0, 4, 1);
-  }
+  sc.my_items = (blockIdx.x < n_groups && tile < n_active) ? (int)((n_groups - 1 - blockIdx.x) / gridDim.x + 1) : 0;
+  sc.total_steps = sc.my_items * n_mob;
 
-  uint8_t* y_blk = smem + kOffY + tile * 4096;
-  uint8_t* c_blk = smem + kOffC + tile * 2048;
-  const uint32_t y_d = umma_desc_lo_ns(smem_u32(y_blk)), c_d = umma_desc_lo_ns(smem_u32(c_blk));
-  const uint32_t w_hid_d = umma_desc_lo(smem_u32(smem + kOffW)), w_last_d = umma_desc_lo(smem_u32(smem + kOffLastW));
-  const uint32_t bias_hid_d = umma_desc_lo_ns(smem_u32(smem + kOffW + 16384)), bias_last_d = umma_desc_lo_ns(smem_u32(smem + kOffLastW + 65536));
-  const uint32_t aux_blk_d = umma_desc_lo_ns(smem_u32(smem + kOffAux + kAuxFirst));
-  const int bar_tile = 1 + tile;                     // named barrier of the tile's 128 threads
-  const int bar_wait = 9 + tile;                     // ... and the one its non-issuing warps sleep in during a GEMM round trip
-  const uint32_t bar_mma = bars + 8 * (BAR_MMA + tile);
-  uint32_t par_mma = 0, par_w = 0;
-  bool w_ready = false;                              // issuing warp: the next GEMM's weight piece is known to have landed
-  int64_t step = 0;
-  int mob_cur = 0;
-  constexpr uint32_t kIdesc = umma_idesc(128, 64);
-
-  // Hand-over of the tile's accumulator / A operand to the tensor core: every thread orders its TMEM accesses before the
-  // barrier; only the issuing warp waits there (the others go straight to the mbarrier of the GEMM being issued).
-  auto hand_over = [&]() {
-    tc_fence_before();
-    if (issuer_warp) named_bar(bar_tile, 128); else named_arrive(bar_tile, 128);
-  };
-  auto wait_mma = [&]() {
-    mbar_wait(bar_mma, par_mma);
-    par_mma ^= 1;
-    tc_fence_after();
-  };
-  // The same for a wait that is expected to be LONG (the dependent GEMM round trips of the chain): only the issuing warp polls
-  // the mbarrier; the other three warps of the tile sleep in a hardware named barrier, which costs no issue slots.  (ncu on the
-  // all-poll version: the YIELD / SYNCS.TRYWAIT / BRA loop is 12.7 % of all executed warp instructions -- a try_wait suspends
-  // for ~100 cycles only.)  The issuer issued the MMAs it waits for, so its tcgen05 fences order them for the other warps.
-  auto wait_mma_long = [&]() {
-#if RNF_T4_WAIT_BAR
-    if (issuer_warp) {
-      mbar_wait(bar_mma, par_mma);
-      tc_fence_before();
-      named_arrive(bar_wait, 128);
-    } else {
-      named_bar(bar_wait, 128);
-    }
-    par_mma ^= 1;
-    tc_fence_after();
-#else
-    wait_mma();
-#endif
-  };
-
-  for (int64_t item = 0; item < my_items; ++item) {
-    const int64_t tile_idx = n_active * (blockIdx.x + item * (int64_t)gridDim.x) + tile;
-    int64_t row = 0, img = 0, g = 0;
-    bool valid = false;
-    float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
-    if (tile_idx < a.n_tiles) {
-      if (GRID) {
-        img = tile_idx / a.tiles_per_image;
-        g = (tile_idx % a.tiles_per_image) * kRows + rowi;
-        valid = g < a.G;
-        row = img * a.G + g;
-        if (valid) {
-          float Gm[9];
-#pragma unroll
-          for (int i = 0; i < 9; ++i) Gm[i] = __ldg(a.R_in + g * 9 + i);
-          if (a.offset != nullptr) {                 // samples = grid @ random_rot (eval.py:439-440)
-            float O[9];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) O[i] = __ldg(a.offset + i);
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-              for (int j = 0; j < 3; ++j)
-                R[3 * i + j] = fmaf(Gm[3 * i + 2], O[6 + j], fmaf(Gm[3 * i + 1], O[3 + j], Gm[3 * i] * O[j]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) R[i] = Gm[i];
-          }
-        }
-      } else {
-        row = tile_idx * kRows + rowi;
-        valid = row < a.N;
-        if (valid) {
-#pragma unroll
-          for (int i = 0; i < 9; ++i) R[i] = __ldg(a.R_in + row * 9 + i);
-          if (a.cond != nullptr) img = a.feat_index != nullptr ? (int64_t)__ldg(a.feat_index + row) : row / a.rows_per_image;
-        }
-      }
-    }
-    const float* cond_img = a.cond != nullptr ? a.cond + img * a.cond_stride : nullptr;
-    float ldj = 0.0f;
-    float dgt = 0.0f;                                  // spread metric: angle of the evaluation point to the image's ground truth
-    if (GRID && a.gt != nullptr && valid) dgt = gt_distance(a.gt + img * a.gt_k * 9, a.gt_k, R);
-
-#pragma unroll 1
-    for (int li = 0; li < a.n_layers; ++li) {
-      const LayerDev L = a.layers[li];
-      if (L.kind != RNF_LAYER_MOBIUS) {
-        const float* W = L.cond_slot >= 0 ? cond_img + (int64_t)a.n_mobius_slots * kH + (int64_t)L.cond_slot * kAffFloats
-                                          : a.weights + L.w_off;
-        affine_family_layer<true>(L, W, R, ldj);
-        continue;
-      }
-      // ================================ Mobius layer ================================
-      const int p0 = L.perm, p1 = (L.perm + 1) % 3, p2 = (L.perm + 2) % 3;
-      float x[3], y[3];
-      Plane P;
-      get_col(R, p0, x);
-      get_col(R, p1, y);
-      make_frame_fast(x, y, P);
-      const float zr = dot3(x, P.r), zv = dot3(x, P.v);   // in-plane coordinates of the moving column
-      const float* cimg = (L.cond_slot >= 0 && cond_img != nullptr) ? cond_img + (int64_t)L.cond_slot * kH : nullptr;
-      const bool c_by_mma = GRID && cimg != nullptr;      // warp- and tile-uniform
-      const float* cadd = GRID ? nullptr : cimg;
+  if (service) {
+    set_max_regs_dec<RNF_T4_SERVICE_REGS>();
+    service_warp<GRID>(a, smem, tmem_base, tile, lane, sc, n_mob, s_moff, s_cnt);
+  } else {
+    set_max_regs_inc<RNF_T4_WORKER_REGS>();
+    const uint32_t tm = tmem_base + (uint32_t)tile * kColsPerTile + ((uint32_t)((warp & 3) * 32) << 16);   // my warp's lane quarter
+    uint8_t* y_blk = smem + kOffY + tile * 4096;
+    uint8_t* c_blk = smem + kOffC + tile * 2048;
+    const int bar_wait = 9 + tile;                     // named barrier: the tile's workers sleep here during a GEMM round trip
+    const uint32_t bar_mma = bars + 8 * (BAR_MMA + tile), bar_ready = bars + 8 * (BAR_READY + tile);
+    uint32_t par_mma = 0;
 #if RNF_TC_TRACE
-      const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && elected && step >= 40 && step < 48;
-      long long* tr = a.trace + ((tile * 8 + (step - 40)) * 32);
+    int64_t step = 0;
 #endif
-      TRACE(0);
-      const int abuf = (int)(step & 1);
-      const int mob_n1 = mob_cur + 1 >= n_mob ? mob_cur + 1 - n_mob : mob_cur + 1;
-      const int mob_n2 = mob_n1 + 1 >= n_mob ? mob_n1 + 1 - n_mob : mob_n1 + 1;
 
-      // ---- my row of the Y block: (1, 1, y_hi, y_lo | y_hi, 1, 1, 0, 0, 0); per-image block in grid mode ----
-      {
-        __half yh[3], yl[3];
+    // Hand-over of the tile's accumulator / A operand / Y block to the service warp: every thread orders its TMEM accesses,
+    // one lane per warp arrives on the tile's mbarrier.  Nobody waits here.
+    auto hand_over = [&]() {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ready);
+    };
+    // Wait for a GEMM that the tile cannot overlap with anything (the dependent round trips of the chain): the workers sleep in a
+    // hardware named barrier, which costs no issue slots; the service warp polls the MMA's mbarrier and arrives.  (ncu on an
+    // all-poll version: the YIELD / SYNCS.TRYWAIT / BRA loop was 12.7 % of all executed warp instructions.)
+    auto wait_mma_long = [&]() {
+      named_bar(bar_wait, 128 + 32);
+      par_mma ^= 1;
+      tc_fence_after();
+    };
+    auto wait_mma = [&]() {                            // a GEMM that ran under the previous chunk's arithmetic: normally complete
+      mbar_wait(bar_mma, par_mma);
+      par_mma ^= 1;
+      tc_fence_after();
+    };
+
+    for (int item = 0; item < sc.my_items; ++item) {
+      const int64_t tile_idx = n_active * (blockIdx.x + item * (int64_t)gridDim.x) + tile;
+      int64_t row = 0, img = 0, g = 0;
+      bool valid = false;
+      float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+      if (tile_idx < a.n_tiles) {
+        if (GRID) {
+          img = tile_idx / a.tiles_per_image;
+          g = (tile_idx % a.tiles_per_image) * kRows + rowi;
+          valid = g < a.G;
+          row = img * a.G + g;
+          if (valid) {
+            float Gm[9];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          yh[i] = __float2half_rn(y[i]);
-          yl[i] = __float2half_rn(y[i] - __half2float(yh[i]));
-        }
-        const __half one = __float2half_rn(1.0f), zero = __float2half_rn(0.0f);
-        uint8_t* yrow = y_blk + (rowi >> 3) * 256 + (rowi & 7) * 16;
-        *reinterpret_cast<uint4*>(yrow) = make_uint4(pack_h2(one, one), pack_h2(yh[0], yh[1]), pack_h2(yh[2], yl[0]), pack_h2(yl[1], yl[2]));
-        *reinterpret_cast<uint4*>(yrow + 128) = make_uint4(pack_h2(yh[0], yh[1]), pack_h2(yh[2], one), pack_h2(one, zero), 0u);
-        if (c_by_mma && rowi < 64) {
-          const float cv = __ldg(cimg + rowi);
-          const __half ch = __float2half_rn(cv);
-          const __half cl = __float2half_rn(cv - __half2float(ch));
-          *reinterpret_cast<uint32_t*>(c_blk + (rowi >> 3) * 256 + (rowi & 7) * 16) = pack_h2(ch, cl);
-        }
-      }
-      fence_proxy_async();
-      hand_over();
-      TRACE(1);
-      // ---- fc_first and three hidden layers: four dependent GEMM round trips ----
-#pragma unroll 1
-      for (int l = 0; l < 4; ++l) {
-        if (issuer_warp) {
-          TRACE(20 + 2 * l);                          // 20 .. 29: time spent waiting for the weight pieces
-          if (!w_ready) {
-            if (l == 0) mbar_wait(bars + 8 * (BAR_AUX_FULL + abuf), (uint32_t)((step >> 1) & 1));
-            else mbar_wait(bars + 8 * (BAR_W_FULL + l - 1), (par_w >> (l - 1)) & 1u);
-          }
-          TRACE(21 + 2 * l);
-          tc_fence_after();
-          if (elect_one_sync()) {
-            const uint32_t d = tm_tile + kColD;
-            if (l == 0) {
-              umma_f16(d, y_d, aux_blk_d + abuf * (kAuxStride >> 4), kDescHiNS, kIdesc, 0);
+            for (int i = 0; i < 9; ++i) Gm[i] = __ldg(a.R_in + g * 9 + i);
+            if (a.offset != nullptr) {                 // samples = grid @ random_rot (eval.py:439-440)
+              float O[9];
+#pragma unroll
+              for (int i = 0; i < 9; ++i) O[i] = __ldg(a.offset + i);
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                  R[3 * i + j] = fmaf(Gm[3 * i + 2], O[6 + j], fmaf(Gm[3 * i + 1], O[3 + j], Gm[3 * i] * O[j]));
             } else {
-              const uint32_t wb = w_hid_d + (l - 1) * (kW1Bytes >> 4);
-              umma_f16(d, y_d, bias_hid_d + (l - 1) * (kW1Bytes >> 4), kDescHiNS, kIdesc, 0);
-              issue_split_ts(d, tm_tile + kColAhi, tm_tile + kColAlo, wb, wb + (8192 >> 4), kIdesc);
+#pragma unroll
+              for (int i = 0; i < 9; ++i) R[i] = Gm[i];
             }
-            if (c_by_mma && (l == 0 || l == 3)) umma_f16(d, y_d, c_d, kDescHiNS, kIdesc, 1);
-            umma_commit(bar_mma);
           }
-          __syncwarp();
-#if RNF_T4_EARLY_W
-          // While this GEMM runs: one non-blocking look at the barrier of the NEXT GEMM's weights (W_{l+1}, then W4), so that the
-          // ~150-cycle mbarrier round trip of an already completed barrier is off the chain's critical path (timeline: 8 such
-          // waits per tile and layer).  Not a blocking wait: the piece may still belong to a slower tile's previous layer.
-          w_ready = mbar_test(bars + 8 * (BAR_W_FULL + l), (par_w >> l) & 1u);
-#else
-          w_ready = false;
-#endif
+        } else {
+          row = tile_idx * kRows + rowi;
+          valid = row < a.N;
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) R[i] = __ldg(a.R_in + row * 9 + i);
+            if (a.cond != nullptr) img = a.feat_index != nullptr ? (int64_t)__ldg(a.feat_index + row) : row / a.rows_per_image;
+          }
         }
-        TRACE(2 + 3 * l);
-        wait_mma_long();
-        TRACE(3 + 3 * l);
-        // a piece is dead once ALL tiles' GEMM that reads it has completed: the last tile to get here refills it
-        if (elected) {
-          if (l == 0) { if ((atomicAdd(&s_cnt[4 + abuf], 1) % n_active) == n_active - 1 && step + 2 < total_steps) load_piece(mob_n2, 4, abuf); }
-          else if ((atomicAdd(&s_cnt[l - 1], 1) % n_active) == n_active - 1 && step + 1 < total_steps) load_piece(mob_n1, l - 1, 0);
-        }
-        const float* ca = (l == 0 || l == 3) ? cadd : nullptr;
-        epilogue64(tm, ca);
-        hand_over();
-        TRACE(4 + 3 * l);
       }
-      // ---- fc_last in four N = 64 chunks through the single accumulator; 16 mixture components per chunk ----
-      auto issue_chunk = [&](int c) {               // issuing warp only, right after the hand-over barrier
-        if (c == 0) {
-          TRACE(28);
-          if (!w_ready) mbar_wait(bars + 8 * (BAR_W_FULL + 3), (par_w >> 3) & 1u);
-          TRACE(29);
-        }
-        tc_fence_after();
-        if (elect_one_sync()) {
-          const uint32_t d = tm_tile + kColD;
-          const uint32_t wb = w_last_d + c * (8192 >> 4);                  // rows 64c .. 64c+63 of the hi plane
-          umma_f16(d, y_d, bias_last_d + c * (2048 >> 4), kDescHiNS, kIdesc, 0);
-          issue_split_ts(d, tm_tile + kColAhi, tm_tile + kColAlo, wb, wb + (32768 >> 4), kIdesc);
-          umma_commit(bar_mma);
-        }
-        __syncwarp();
-#if RNF_T4_EARLY_W
-        if (c == 3) {                                  // next layer's fc_first block (aux buffer of step + 1)
-          w_ready = step + 1 < total_steps && mbar_test(bars + 8 * (BAR_AUX_FULL + (abuf ^ 1)), (uint32_t)(((step + 1) >> 1) & 1));
-        }
-#endif
-      };
-      if (issuer_warp) issue_chunk(0);
-      f32x2 S_sp2 = 0ull, S_th2 = 0ull, S_f2 = 0ull;   // packed partial sums (even | odd components)
-      // W4 is dead the moment the last chunk's MMAs have completed (not after the arithmetic on it): the last tile to see that
-      // refills it.  (Refilling W4 chunk by chunk removes the leaders' remaining wait for it but lets three tiles fall into
-      // lock step: 222 M instead of 238 M rot/s -- the coupling through this one piece keeps the tiles in two anti-phase pairs.)
-#define W4_DONE() do { if (c == 3 && elected && (atomicAdd(&s_cnt[3], 1) % n_active) == n_active - 1 && step + 1 < total_steps) load_piece(mob_n1, 3, 0); } while (0)
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-#if RNF_T4_NP == 4
-        float buf[32];
-        wait_mma();
-        TRACE(14 + c);
-        W4_DONE();
-        tmem_ld32(tm + kColD, buf);
-        mixture_pairs<4, true>(P, zr, zv, buf, S_sp2, S_th2, S_f2);
-        tmem_ld32(tm + kColD + 32, buf);
-        if (c < 3) {                                  // accumulator drained: the next chunk runs under the math below
-          hand_over();
-          if (issuer_warp) issue_chunk(c + 1);
-        }
-        mixture_pairs<4, true>(P, zr, zv, buf, S_sp2, S_th2, S_f2);
-      }
-#else
-        float buf0[16], buf1[16];
-        if (c == 2) TRACE(30);                        // 30 / 31: how long chunk 2's MMAs keep the tile waiting
-        if (c == 0) wait_mma_long(); else wait_mma();  // chunks 1..3 ran under the previous chunk's arithmetic: no spinning
-        if (c == 2) TRACE(31);
-        TRACE(14 + c);
-        W4_DONE();
-        tmem_ld16_async(tm + kColD, buf0);
-        tmem_ld16_async(tm + kColD + 16, buf1);
-        tmem_ld_wait16(buf0);
-        mixture_pairs<2, true>(P, zr, zv, buf0, S_sp2, S_th2, S_f2);
-        tmem_ld16_async(tm + kColD + 32, buf0);
-        tmem_ld_wait16(buf1);
-        T4_YIELD(2);
-        mixture_pairs<2, true>(P, zr, zv, buf1, S_sp2, S_th2, S_f2);
-        tmem_ld16_async(tm + kColD + 48, buf1);
-        tmem_ld_wait16(buf0);
-        tmem_ld_wait16(buf1);
-        if (c < 3) {                                  // accumulator drained: the next chunk runs under the math below
-          hand_over();
-          if (issuer_warp) issue_chunk(c + 1);
-        }
-        T4_YIELD(1);
-        mixture_pairs<2, true>(P, zr, zv, buf0, S_sp2, S_th2, S_f2);
-        T4_YIELD(2);
-        mixture_pairs<2, true>(P, zr, zv, buf1, S_sp2, S_th2, S_f2);
-      }
-#endif
-#undef W4_DONE
-      if (issuer_warp) par_w ^= 0xFu;
-      TRACE(18);
-      float nx[3], nz[3];
-      const float S_sp = hsum(S_sp2), S_th = hsum(S_th2), S_f = hsum(S_f2);
-      const float inv_sp = rcp_nr(S_sp);
-      circle_point_fast(P.r, P.v, mixture_angle(S_th, inv_sp), nx);
-      ldj += log_fast(S_f * inv_sp);
-      cross3(nx, y, nz);
-      normalize3_fast(nz);
-      set_col(R, p0, nx);
-      set_col(R, p2, nz);
-      TRACE(19);
-      ++step;
-      mob_cur = mob_n1;
-    }
+      const float* cond_img = a.cond != nullptr ? a.cond + img * a.cond_stride : nullptr;
+      float ldj = 0.0f;
+      float dgt = 0.0f;                                  // spread metric: angle of the evaluation point to the image's ground truth
+      if (GRID && a.gt != nullptr && valid) dgt = gt_distance(a.gt + img * a.gt_k * 9, a.gt_k, R);
 
-    // ================================ outputs ================================
-    if (!GRID) {
-      if (valid) {
+#pragma unroll 1
+      for (int li = 0; li < a.n_layers; ++li) {
+        const LayerDev L = a.layers[li];
+        if (L.kind != RNF_LAYER_MOBIUS) {
+          const float* W = L.cond_slot >= 0 ? cond_img + (int64_t)a.n_mobius_slots * kH + (int64_t)L.cond_slot * kAffFloats
+                                            : a.weights + L.w_off;
+          affine_family_layer<true>(L, W, R, ldj);
+          continue;
+        }
+        // ================================ Mobius layer ================================
+        const int p0 = L.perm, p1 = (L.perm + 1) % 3, p2 = (L.perm + 2) % 3;
+        float x[3], y[3];
+        Plane P;
+        get_col(R, p0, x);
+        get_col(R, p1, y);
+        make_frame_fast(x, y, P);
+        const float zr = dot3(x, P.r), zv = dot3(x, P.v);   // in-plane coordinates of the moving column
+        const float* cimg = (L.cond_slot >= 0 && cond_img != nullptr) ? cond_img + (int64_t)L.cond_slot * kH : nullptr;
+        const bool c_by_mma = GRID && cimg != nullptr;      // warp- and tile-uniform (the service warp derives the same flag)
+        const float* cadd = GRID ? nullptr : cimg;
+#if RNF_TC_TRACE
+        const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && (warp & 3) == 0 && lane == 0 && step >= 40 && step < 48;
+        long long* tr = a.trace + ((tile * 8 + (step - 40)) * 32);
+#endif
+        TRACE(0);
+
+        // ---- my row of the Y block: (1, 1, y_hi, y_lo | y_hi, 1, 1, 0, 0, 0); per-image block in grid mode ----
+        {
+          __half yh[3], yl[3];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) a.R_out[row * 9 + i] = R[i];
-        a.ldj_out[row] = ldj;
+          for (int i = 0; i < 3; ++i) {
+            yh[i] = __float2half_rn(y[i]);
+            yl[i] = __float2half_rn(y[i] - __half2float(yh[i]));
+          }
+          const __half one = __float2half_rn(1.0f), zero = __float2half_rn(0.0f);
+          uint8_t* yrow = y_blk + (rowi >> 3) * 256 + (rowi & 7) * 16;
+          *reinterpret_cast<uint4*>(yrow) = make_uint4(pack_h2(one, one), pack_h2(yh[0], yh[1]), pack_h2(yh[2], yl[0]), pack_h2(yl[1], yl[2]));
+          *reinterpret_cast<uint4*>(yrow + 128) = make_uint4(pack_h2(yh[0], yh[1]), pack_h2(yh[2], one), pack_h2(one, zero), 0u);
+          if (c_by_mma && rowi < 64) {
+            const float cv = __ldg(cimg + rowi);
+            const __half ch = __float2half_rn(cv);
+            const __half cl = __float2half_rn(cv - __half2float(ch));
+            *reinterpret_cast<uint32_t*>(c_blk + (rowi >> 3) * 256 + (rowi & 7) * 16) = pack_h2(ch, cl);
+          }
+        }
+        fence_proxy_async();
+        hand_over();
+        TRACE(1);
+        // ---- fc_first and three hidden layers: four dependent GEMM round trips ----
+#pragma unroll 1
+        for (int l = 0; l < 4; ++l) {
+          wait_mma_long();
+          TRACE(3 + 3 * l);
+          const float* ca = (l == 0 || l == 3) ? cadd : nullptr;
+          epilogue64(tm, ca);
+          hand_over();
+          TRACE(4 + 3 * l);
+        }
+        // ---- fc_last in four N = 64 chunks through the single accumulator; 16 mixture components per chunk ----
+        f32x2 S_sp2 = 0ull, S_th2 = 0ull, S_f2 = 0ull;   // packed partial sums (even | odd components)
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float buf0[16], buf1[16];
+          if (c == 0) wait_mma_long(); else wait_mma();  // chunks 1..3 ran under the previous chunk's arithmetic: no spinning
+          TRACE(14 + c);
+          tmem_ld16_async(tm + kColD, buf0);
+          tmem_ld16_async(tm + kColD + 16, buf1);
+          tmem_ld_wait16(buf0);
+          mixture_pairs<2, true>(P, zr, zv, buf0, S_sp2, S_th2, S_f2);
+          tmem_ld16_async(tm + kColD + 32, buf0);
+          tmem_ld_wait16(buf1);
+          mixture_pairs<2, true>(P, zr, zv, buf1, S_sp2, S_th2, S_f2);
+          tmem_ld16_async(tm + kColD + 48, buf1);
+          tmem_ld_wait16(buf0);
+          tmem_ld_wait16(buf1);
+          if (c < 3) hand_over();                        // accumulator drained: the next chunk runs under the math below
+          mixture_pairs<2, true>(P, zr, zv, buf0, S_sp2, S_th2, S_f2);
+          mixture_pairs<2, true>(P, zr, zv, buf1, S_sp2, S_th2, S_f2);
+        }
+        TRACE(18);
+        float nx[3], nz[3];
+        const float S_sp = hsum(S_sp2), S_th = hsum(S_th2), S_f = hsum(S_f2);
+        const float inv_sp = rcp_nr(S_sp);
+        circle_point_fast(P.r, P.v, mixture_angle(S_th, inv_sp), nx);
+        ldj += log_fast(S_f * inv_sp);
+        cross3(nx, y, nz);
+        normalize3_fast(nz);
+        set_col(R, p0, nx);
+        set_col(R, p2, nz);
+        TRACE(19);
+#if RNF_TC_TRACE
+        ++step;
+#endif
       }
-    } else if (tile_idx < a.n_tiles) {
-      float lp = ldj;
-      if (a.fisher_A != nullptr) {
-        float tr = 0.0f;
+
+      // ================================ outputs ================================
+      if (!GRID) {
+        if (valid) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) tr = fmaf(__ldg(a.fisher_A + img * 9 + i), R[i], tr);
-        lp += tr - __ldg(a.fisher_c + img);
-      }
-      if (!valid) lp = -INFINITY;
-      if (a.logp_out != nullptr && valid) a.logp_out[row] = lp;
-      float* s_v = reinterpret_cast<float*>(smem + kOffRed + tile * 128);
-      long long* s_i = reinterpret_cast<long long*>(smem + kOffRed + tile * 128 + 32);
-      const int w4 = warp & 3;
-      const int bar_red = 5 + tile;
-      float bv = lp;
-      long long bi = valid ? (long long)g : 0x7fffffffffffffffLL;
+          for (int i = 0; i < 9; ++i) a.R_out[row * 9 + i] = R[i];
+          a.ldj_out[row] = ldj;
+        }
+      } else if (tile_idx < a.n_tiles) {
+        float lp = ldj;
+        if (a.fisher_A != nullptr) {
+          float tr = 0.0f;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-      }
-      if (lane == 0) { s_v[w4] = bv; s_i[w4] = bi; }
-      named_bar(bar_red, 128);
-      bv = s_v[0]; bi = s_i[0];
+          for (int i = 0; i < 9; ++i) tr = fmaf(__ldg(a.fisher_A + img * 9 + i), R[i], tr);
+          lp += tr - __ldg(a.fisher_c + img);
+        }
+        if (!valid) lp = -INFINITY;
+        if (a.logp_out != nullptr && valid) a.logp_out[row] = lp;
+        float* s_v = reinterpret_cast<float*>(smem + kOffRed + tile * 128);
+        long long* s_i = reinterpret_cast<long long*>(smem + kOffRed + tile * 128 + 32);
+        const int w4 = warp & 3;
+        const int bar_red = 5 + tile;
+        float bv = lp;
+        long long bi = valid ? (long long)g : 0x7fffffffffffffffLL;
 #pragma unroll
-      for (int w = 1; w < 4; ++w) {
-        const float ov = s_v[w];
-        const long long oi = s_i[w];
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-      }
-      const float m = bv;
-      float e = (valid && m > -INFINITY) ? expf(lp - m) : 0.0f;
-      float ed = e * dgt;
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_v[w4] = bv; s_i[w4] = bi; }
+        named_bar(bar_red, 128);
+        bv = s_v[0]; bi = s_i[0];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        e += __shfl_xor_sync(0xffffffffu, e, o);
-        ed += __shfl_xor_sync(0xffffffffu, ed, o);
+        for (int w = 1; w < 4; ++w) {
+          const float ov = s_v[w];
+          const long long oi = s_i[w];
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        const float m = bv;
+        float e = (valid && m > -INFINITY) ? expf(lp - m) : 0.0f;
+        float ed = e * dgt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          e += __shfl_xor_sync(0xffffffffu, e, o);
+          ed += __shfl_xor_sync(0xffffffffu, ed, o);
+        }
+        named_bar(bar_red, 128);
+        if (lane == 0) { s_v[w4] = e; s_v[4 + w4] = ed; }
+        named_bar(bar_red, 128);
+        if (rowi == 0) {
+          const float s = (s_v[0] + s_v[1]) + (s_v[2] + s_v[3]);
+          float* p = a.part + tile_idx * kPartStride;
+          p[0] = m;
+          p[1] = s;
+          p[4] = (s_v[4] + s_v[5]) + (s_v[6] + s_v[7]);
+          p[2] = __int_as_float((int)(bi & 0xffffffffLL));
+          p[3] = __int_as_float((int)(bi >> 32));
+        }
+        named_bar(bar_red, 128);
       }
-      named_bar(bar_red, 128);
-      if (lane == 0) { s_v[w4] = e; s_v[4 + w4] = ed; }
-      named_bar(bar_red, 128);
-      if (rowi == 0) {
-        const float s = (s_v[0] + s_v[1]) + (s_v[2] + s_v[3]);
-        float* p = a.part + tile_idx * kPartStride;
-        p[0] = m;
-        p[1] = s;
-        p[4] = (s_v[4] + s_v[5]) + (s_v[6] + s_v[7]);
-        p[2] = __int_as_float((int)(bi & 0xffffffffLL));
-        p[3] = __int_as_float((int)(bi >> 32));
-      }
-      named_bar(bar_red, 128);
     }
   }
 
@@ -660,7 +626,7 @@ cudaError_t launch_flow_t4(const FlowArgs& a_in, int sm_count, cudaStream_t st) 
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc);
   if (e != cudaSuccess) return e;
   if (a.n_tiles <= 0) return cudaSuccess;
-  a.t4_active = kTiles == 4 ? pick_active_tiles(a.n_tiles, sm_count) : kTiles;
+  a.t4_active = pick_active_tiles(a.n_tiles, sm_count);
   if (const char* force = getenv("RNF_T4_ACTIVE")) {         // measurement override (tools/): tiles in flight, 1..4
     const int v = atoi(force);
     if (v >= 1 && v <= kTiles) a.t4_active = v;
