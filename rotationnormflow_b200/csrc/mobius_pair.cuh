@@ -14,6 +14,12 @@
 #pragma once
 #include "mobius_fast.cuh"
 
+#ifndef RNF_MIX_CLAMP
+#define RNF_MIX_CLAMP 0          // 1: logit clamped at 127 (log2 units) before ex2 instead of the  t > 28.85 ? t : ...  select
+#endif
+#ifndef RNF_ASIN_DEG
+#define RNF_ASIN_DEG 6           // degree of P in asin(m) = m + m s P(s): 6 -> 4.6e-8, 5 -> 8.9e-8 max abs error in fp32 Horner form
+#endif
 #ifndef RNF_MIX_RSQ
 #define RNF_MIX_RSQ 1            // forward mixture: rsqrt + asin (8 SFU operations per pair) instead of two reciprocals + atan (10)
 #endif
@@ -67,6 +73,14 @@ __device__ __forceinline__ f32x2 asin_unit2_s(f32x2 m, f32x2 s);
 __device__ __forceinline__ f32x2 asin_unit2(f32x2 m) { return asin_unit2_s(m, mul2(m, m)); }
 // ... with s = m^2 supplied by the caller
 __device__ __forceinline__ f32x2 asin_unit2_s(f32x2 m, f32x2 s) {
+#if RNF_ASIN_DEG == 5
+  f32x2 p = bc(0.11149732023477554f);
+  p = fma2(p, s, bc(-0.07131081074476242f));
+  p = fma2(p, s, bc(0.07036406546831131f));
+  p = fma2(p, s, bc(0.036296285688877106f));
+  p = fma2(p, s, bc(0.07581107318401337f));
+  p = fma2(p, s, bc(0.1666388362646103f));
+#else
   f32x2 p = bc(0.12371734529733658f);
   p = fma2(p, s, bc(-0.11529727280139923f));
   p = fma2(p, s, bc(0.09339626878499985f));
@@ -74,6 +88,7 @@ __device__ __forceinline__ f32x2 asin_unit2_s(f32x2 m, f32x2 s) {
   p = fma2(p, s, bc(0.04762402921915054f));
   p = fma2(p, s, bc(0.07478351145982742f));
   p = fma2(p, s, bc(0.16667234897613525f));
+#endif
   return fma2(mul2(p, s), m, m);
 }
 
@@ -112,7 +127,13 @@ __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv
     f32x2 t[NP], e[NP], big[NP], small[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
+#if RNF_MIX_CLAMP
+      // lg2(1 + 2^t) = t to fp32 precision for t > 25, so the only job of the reference's  x > 20 ? x : log1p(exp(x))  branch
+      // (torch softplus threshold) is to avoid the overflow of 2^t: clamp t instead of selecting afterwards.
+      t[j] = pk(fminf(raw[8 * j], 127.0f), fminf(raw[8 * j + 1], 127.0f));
+#else
       t[j] = pk(raw[8 * j], raw[8 * j + 1]);
+#endif
       RNF_MAP2(e[j], t[j], ex2_approx);
     }
 #pragma unroll
@@ -136,7 +157,11 @@ __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv
       float tl, th, el, eh, bl, bh, sl, sh;
       upk(t[j], tl, th); upk(e[j], el, eh); upk(big[j], bl, bh); upk(small[j], sl, sh);
       const float vl = el < 0.0078125f ? sl : bl, vh = eh < 0.0078125f ? sh : bh;
+#if RNF_MIX_CLAMP
+      sp[j] = pk(vl, vh);
+#else
       sp[j] = pk(tl > 28.853900817779268f ? tl : vl, th > 28.853900817779268f ? th : vh);
+#endif
     }
   }
   if (FWD) {

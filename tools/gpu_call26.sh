@@ -1,0 +1,10 @@
+#!/bin/bash
+# half-epilogue hand-over: smoke + parity with the product build, A/B of the variants, phase timeline of the new kernel
+mkdir -p gpurun_out
+timeout 150 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke26.log 2>&1; rc=$?; echo "smoke rc=$rc"; tail -2 gpurun_out/smoke26.log
+if [ $rc -ne 0 ]; then exit 1; fi
+timeout 500 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --timeout 120 -k "forward or grid" 2>&1 | tail -3
+for rep in 1 2; do PREFIX=x_ STEPS=5 TMO=100 bash tools/ab2.sh; done 2>&1 | tee gpurun_out/ab_half.txt
+cp rotationnormflow_b200/librnf_b200.so tools/_build/.product.so; cp tools/_build/t_trace.so rotationnormflow_b200/librnf_b200.so
+timeout 120 python tools/tc_timeline.py > gpurun_out/r02_t4_timeline_service.txt 2>&1; tail -16 gpurun_out/r02_t4_timeline_service.txt | cut -c1-330
+cp tools/_build/.product.so rotationnormflow_b200/librnf_b200.so

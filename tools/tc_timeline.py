@@ -8,7 +8,7 @@ import bench
 from rotationnormflow_b200 import _cabi, grid as rgrid
 from rotationnormflow_b200.flow import _program
 
-cfg, flow = bench.build_flow()
+cfg, flow = bench.build_flow("symsol", feature_dim=2048)
 flow = flow.cuda().eval()
 lib = _cabi.load()
 raw = C.CDLL(_cabi.library_path())
@@ -21,8 +21,10 @@ out = flow.grid_log_prob(G, feat, mlp_mode=os.environ.get("RNF_TRACE_MODE", "tc"
 torch.cuda.synchronize()
 mode = os.environ.get("RNF_TRACE_MODE", "tc")
 if mode == "tc":
-    names = {0: "start", 1: "yblk", 2: "iss0", 3: "mma0", 4: "epi0", 5: "iss1", 6: "mma1", 7: "epi1", 8: "iss2", 9: "mma2", 10: "epi2",
-             11: "iss3", 12: "mma3", 13: "epi3", 14: "chunk0", 15: "chunk1", 16: "chunk2", 17: "chunk3", 18: "mix", 19: "end"}
+    # worker view (warp quarter 0 of each tile): gemmN = hand-over -> woken up after GEMM N (issue by the service warp + MMAs),
+    # epiN = epilogue of GEMM N incl. both half hand-overs, chunkN = wait + drain of fc_last chunk N (incl. the arithmetic before it)
+    names = {0: "start", 1: "yblk", 3: "gemm0", 4: "epi0", 6: "gemm1", 7: "epi1", 9: "gemm2", 10: "epi2",
+             12: "gemm3", 13: "epi3", 14: "chunk0", 15: "chunk1", 16: "chunk2", 17: "chunk3", 18: "mix", 19: "end"}
 else:
     names = {0: "start", 1: "turn", 2: "prologue", 3: "bar1", 4: "iss1", 5: "mma1", 6: "epi1", 7: "bar2", 8: "iss2", 9: "mma2", 10: "epi2",
              11: "bar3", 12: "iss3", 13: "mma3", 14: "epi3", 15: "bar4", 16: "iss4", 17: "mmaA", 18: "mix", 19: "xchg", 20: "end"}
@@ -34,6 +36,6 @@ for s in range(2, 6):
     for tile in range(n_tiles):
         row = t[tile, s]
         base = int(row[0])
-        print(f"step {40+s} tile {tile}: start @{base - t0:7d} | " + " ".join(f"{names[i]}+{int(row[i]) - int(row[i-1])}" for i in range(1, last + 1))
-              + f" | total {int(row[last]) - base}"
-              + (" | weight waits " + " ".join(str(int(row[21 + 2 * k]) - int(row[20 + 2 * k])) for k in range(5)) + f" | chunk-2 MMA wait {int(row[31]) - int(row[30])}" if mode == "tc" else ""))
+        idx = sorted(names)
+        print(f"step {40+s} tile {tile}: start @{base - t0:7d} | " + " ".join(f"{names[i]}+{int(row[i]) - int(row[j])}" for j, i in zip(idx[:-1], idx[1:]))
+              + f" | total {int(row[last]) - base}")
