@@ -85,16 +85,20 @@ def test_packed_asin_polynomial_accuracy():
     float32 Horner emulation of the polynomial read back from the header, against asin on [0, 1/sqrt 2]."""
     src = open(os.path.join(ROOT, "rotationnormflow_b200", "csrc", "mobius_pair.cuh")).read()
     body = src[src.index("f32x2 asin_unit2"):src.index("// atan on the half-angle range")]
-    co = [float(v) for v in re.findall(r"bc\((-?[0-9.e-]+)f\)", body)]          # highest power first
-    assert len(co) == 7
-    m = np.linspace(0, 0.70711, 1_000_001).astype(np.float32)
-    s = (m.astype(np.float64) * m).astype(np.float32)
-    p = np.full_like(s, np.float32(co[0]))
-    for c in co[1:]:
-        p = _fma32(p, s, np.float32(c))
-    ps = (p.astype(np.float64) * s).astype(np.float32)
-    res = (ps.astype(np.float64) * m + m).astype(np.float32)
-    assert np.abs(res.astype(np.float64) - np.arcsin(m.astype(np.float64))).max() < 6e-8
+    # the shipped degree-6 polynomial (#else branch) and the degree-5 experiment (RNF_ASIN_DEG == 5), highest power first
+    deg5, deg6 = body[body.index("#if RNF_ASIN_DEG == 5"):body.index("#else")], body[body.index("#else"):body.index("#endif")]
+    assert "#define RNF_ASIN_DEG 6" in src
+    for part, n, bound in ((deg6, 7, 6e-8), (deg5, 6, 1e-7)):
+        co = [float(v) for v in re.findall(r"bc\((-?[0-9.e-]+)f\)", part)]
+        assert len(co) == n
+        m = np.linspace(0, 0.70711, 1_000_001).astype(np.float32)
+        s = (m.astype(np.float64) * m).astype(np.float32)
+        p = np.full_like(s, np.float32(co[0]))
+        for c in co[1:]:
+            p = _fma32(p, s, np.float32(c))
+        ps = (p.astype(np.float64) * s).astype(np.float32)
+        res = (ps.astype(np.float64) * m + m).astype(np.float32)
+        assert np.abs(res.astype(np.float64) - np.arcsin(m.astype(np.float64))).max() < bound
     # unit vector: atan(min / max) == asin(min)
     t = np.linspace(0, np.pi / 4, 1001)
     assert np.abs(np.arctan(np.sin(t) / np.cos(t)) - np.arcsin(np.sin(t))).max() < 1e-15

@@ -218,6 +218,33 @@ def test_edge_cases():
     assert (before - after).abs().max() > 1e-4
 
 
+def test_tiles_in_flight_do_not_change_results(monkeypatch):
+    """flow_t4 picks the number of tile slots (1..4, each with its own service warp) per launch; a rotation's arithmetic does not
+    depend on the slot it lands in, so every choice gives bit-identical outputs -- also across several rounds per SM and with a
+    ragged last tile group (launches of 1 .. 3 * 148 * 4 + 5 tiles)."""
+    g = golden("s_symsol")
+    m = _product(g)
+    gen = torch.Generator().manual_seed(11)
+    for n in (300, 128 * 148 * 2 + 77, 128 * (3 * 148 * 4 + 5) - 9):
+        R = orc.random_rotations(n, gen).float().cuda()
+        f = g.feat[:1].cuda().repeat(n, 1) if n < 4096 else None
+        outs = []
+        for act in ("", "1", "2", "3", "4"):
+            if act:
+                monkeypatch.setenv("RNF_T4_ACTIVE", act)
+            else:
+                monkeypatch.delenv("RNF_T4_ACTIVE", raising=False)
+            with torch.no_grad():
+                if f is not None:
+                    outs.append(m(R, f, mlp_mode="tc"))
+                else:                                            # one image for all rows: the broadcast-aware entry point
+                    outs.append(m(R, g.feat[:1].cuda(), feature_index=torch.zeros(n, dtype=torch.int32, device="cuda"), mlp_mode="tc"))
+        monkeypatch.delenv("RNF_T4_ACTIVE", raising=False)
+        for Rn, ln in outs[1:]:
+            assert torch.equal(Rn, outs[0][0]) and torch.equal(ln, outs[0][1])
+        assert torch.isfinite(outs[0][1]).all()
+
+
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("kw", [dict(layers=1), dict(layers=2), dict(layers=3, frequent_permute=1), dict(layers=2, dist="noflow"),
                                 dict(layers=1, first_affine=0), dict(layers=2, condition=1, feature_dim=16, last_affine=1)],
