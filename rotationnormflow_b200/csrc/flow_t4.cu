@@ -52,7 +52,7 @@ namespace {
 #define RNF_T4_SVC_HINT_NS 0     // suspend-time hint of the service warps' mbarrier waits (0 = default try_wait)
 #endif
 #ifndef RNF_T4_DIRECT_WAIT_NS
-#define RNF_T4_DIRECT_WAIT_NS 0  // > 0: workers wait for chain GEMMs on the MMA mbarrier themselves (try_wait with this hint) instead of the named barrier
+#define RNF_T4_DIRECT_WAIT_NS 2000  // > 0: workers wait for chain GEMMs on the MMA mbarrier themselves (try_wait with this hint) instead of the named barrier
 #endif
 #ifndef RNF_T4_SVC_NAP_NS
 #define RNF_T4_SVC_NAP_NS 0      // service warp: nanosleep between polls of waits that are NOT on a tile's critical path
