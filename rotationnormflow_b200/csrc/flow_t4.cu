@@ -490,9 +490,10 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ready2);
     };
-    // Wait for a GEMM that the tile cannot overlap with anything (the dependent round trips of the chain): the workers sleep in a
-    // hardware named barrier, which costs no issue slots; the service warp polls the MMA's mbarrier and arrives.  (ncu on an
-    // all-poll version: the YIELD / SYNCS.TRYWAIT / BRA loop was 12.7 % of all executed warp instructions.)
+    // Wait for a GEMM that the tile cannot overlap with anything (the dependent round trips of the chain).  Default: every worker
+    // warp watches the MMA's mbarrier itself (try_wait with a suspend hint).  Alternative (RNF_T4_DIRECT_WAIT_NS = 0): the workers
+    // sleep in a hardware named barrier that the service warp arrives on once its own poll of the mbarrier succeeds -- no polling
+    // by the workers, but a second wake-up hop on the critical path (measured ~1 % slower in cycles, tools/ab_ncu.sh).
     auto wait_mma_long = [&]() {
 #if RNF_T4_DIRECT_WAIT_NS > 0
       mbar_wait_hint<RNF_T4_DIRECT_WAIT_NS>(bar_mma, par_mma);
