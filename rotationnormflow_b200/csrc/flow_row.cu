@@ -33,6 +33,9 @@ namespace {
 #define TRACE(i) do { } while (0)
 #endif
 
+#ifndef RNF_ROW_SPLIT_PACKED
+#define RNF_ROW_SPLIT_PACKED 1
+#endif
 #ifndef RNF_INV_NEWTON
 #define RNF_INV_NEWTON 1         // inverse: locate the root with Newton steps, then replay the reference's 15 halvings (see below)
 #endif
@@ -66,7 +69,20 @@ __device__ __forceinline__ void store_a32(uint8_t* a_hi, uint8_t* a_lo, int r, i
   for (int c = 0; c < 4; ++c) {
     uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) relu_split2(v[8 * c + 2 * e], v[8 * c + 2 * e + 1], hi[e], lo[e]);
+    for (int e = 0; e < 4; ++e) {
+#if RNF_ROW_SPLIT_PACKED
+      // as in flow_t4.cu: truncation by mask + packed subtract (5 instructions per pair instead of 6 with two conversions back and
+      // two scalar subtracts); this kernel runs at the per-warp issue cadence, so an instruction less is time less
+      const float x0 = v[8 * c + 2 * e], x1 = v[8 * c + 2 * e + 1];
+      asm("cvt.rz.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi[e]) : "f"(x1), "f"(x0));
+      const float m0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u), m1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+      float d0, d1;
+      upk(sub2(pk(x0, x1), pk(m0, m1)), d0, d1);
+      asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo[e]) : "f"(d1), "f"(d0));
+#else
+      relu_split2(v[8 * c + 2 * e], v[8 * c + 2 * e + 1], hi[e], lo[e]);
+#endif
+    }
     const int off = rbase + (((4 * h + c) ^ (r & 7)) << 4);
     *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -297,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
             float h0[32];
             tmem_ld32(tm + 64 + 32 * h, h0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] += h0[j];
+            for (int j = 0; j < 32; j += 2) upk(add2(pk(acc[j], acc[j + 1]), pk(h0[j], h0[j + 1])), acc[j], acc[j + 1]);
           }
           store_a32(a_hi, a_lo, rowi, h, acc);
         }
