@@ -39,6 +39,9 @@ namespace {
 #ifndef RNF_INV_NEWTON
 #define RNF_INV_NEWTON 1         // inverse: locate the root with Newton steps, then replay the reference's 15 halvings (see below)
 #endif
+#ifndef RNF_INV_PREDICT
+#define RNF_INV_PREDICT 1         // inverse: stop the Newton iteration on the PREDICTED error of the next iterate (one evaluation less per layer)
+#endif
 #ifndef RNF_INV_DELTA
 #define RNF_INV_DELTA 1          // inverse: theta_k = t + 2 asin(sin delta_k) (no quadrant logic), see mobius_pair.cuh probe_delta_pairs
 #endif
@@ -439,6 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
         {
           float a_ = lo, b_ = hi;
           bool conv = false;
+          float prev = 0.0f;                          // |Newton step| of the previous iteration (0: none, or a bisection step)
 #pragma unroll 1
           for (int it = 0; it < 10; ++it) {
             float dF;
@@ -448,9 +452,19 @@ __global__ void __launch_bounds__(kThreads, 1) flow_row_kernel(const FlowArgs a)
               if (F < 0.0f) a_ = ts; else b_ = ts;
               dFs = dF;
               const float step = F / dF;
-              conv = fabsf(step) < 1e-5f;               // quadratic convergence: the error after this step is ~step^2
+              const float as = fabsf(step);
+              conv = as < 1e-5f;                        // quadratic convergence: the error after this step is ~step^2
+#if RNF_INV_PREDICT
+              // ... and how far "~" is can be read off the last two steps: e_{k+1} = C e_k^2 with C = |F''/2F'| ~ |s_k| / s_{k-1}^2
+              // once the iteration contracts (s_k = e_k up to the much smaller e_{k+1}).  Stop as soon as the error PREDICTED after
+              // this step is below 5e-8 -- the fp32 evaluation noise of F keeps t* from being better than ~1e-7 anyway, and the
+              // replay below evaluates explicitly whenever a midpoint is within 2e-6 / F' >= 3.5e-7 of t*.  Saves the evaluation
+              // whose only result would be "the step is now below 1e-5" (typically the fourth).
+              if (prev > 0.0f && as < 1e-2f) conv = conv || fmaxf(as / (prev * prev), 2.0f) * as * as < 5e-8f;
+#endif
               float tn = ts - step;
-              if (!conv && !(tn > a_ && tn < b_)) tn = 0.5f * (a_ + b_);
+              prev = as;
+              if (!conv && !(tn > a_ && tn < b_)) { tn = 0.5f * (a_ + b_); prev = 0.0f; }
               ts = tn;
             }
             if (__all_sync(0xffffffffu, conv)) { newton_ok = true; break; }
