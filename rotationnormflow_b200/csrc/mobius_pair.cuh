@@ -122,7 +122,8 @@ __device__ __forceinline__ f32x2 atan_half2(f32x2 q) {
 // -- one division, no octant selects, and the angle does not wait for f.  The log-det term needs
 //     f = (1 - |w'|^2) / |z - w'|^2 = (u^2 - |(a',b')|^2) / |D|^2,   |D|^2 = Dn^2 + b'^2.
 // Accumulates (sum w, sum w atan q, sum w f) as packed partial sums (a-components in the low, b in the high word).
-// !FWD: accumulates sum w and overwrites raw with the prepared parameters (-alpha', -beta', 1 - |w'|^2, weight).
+// !FWD: accumulates sum w (S_sp), sum w (-alpha') (S_at), sum w (-beta') (S_f) and overwrites raw with the prepared parameters
+// (-alpha', -beta', 1 - |w'|^2, weight).
 template <int NP, bool FWD>
 __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv, float* raw, f32x2& S_sp, f32x2& S_at, f32x2& S_f) {
   f32x2 sp[NP], ap[NP], bp[NP], bb[NP], n2[NP], u[NP], rt[NP];
@@ -221,6 +222,8 @@ __device__ __forceinline__ void mixture_pairs(const Plane& P, float zr, float zv
       const f32x2 nal = mul2(ap[j], nrc), nbe = mul2(bp[j], nrc);
       const f32x2 omw = fma2(fma2(nal, nal, mul2(nbe, nbe)), bc(-1.0f), bc(1.0f));      // 1 - |w'|^2
       S_sp = add2(S_sp, sp[j]);
+      S_at = fma2(sp[j], nal, S_at);                 // sum weight (-alpha'), sum weight (-beta'): the weighted mean centre, from which the
+      S_f = fma2(sp[j], nbe, S_f);                   // inverse direction takes the starting point of its root search (flow_row.cu)
       upk(nal, raw[8 * j], raw[8 * j + 1]);
       upk(nbe, raw[8 * j + 2], raw[8 * j + 3]);
       upk(omw, raw[8 * j + 4], raw[8 * j + 5]);
