@@ -45,8 +45,17 @@ namespace {
 #ifndef RNF_T4_SPLIT_MASK
 #define RNF_T4_SPLIT_MASK 1
 #endif
+#ifndef RNF_T4_HALF_EPI
+#define RNF_T4_HALF_EPI 0        // 1: hand each half of an epilogue's A operand over on its own (first K steps of the next GEMM issue early)
+#endif
+#ifndef RNF_T4_SVC_HINT_NS
+#define RNF_T4_SVC_HINT_NS 0     // suspend-time hint of the service warps' mbarrier waits (0 = default try_wait)
+#endif
 #ifndef RNF_T4_DIRECT_WAIT_NS
 #define RNF_T4_DIRECT_WAIT_NS 2000  // > 0: workers wait for chain GEMMs on the MMA mbarrier themselves (try_wait with this hint) instead of the named barrier
+#endif
+#ifndef RNF_T4_SVC_NAP_NS
+#define RNF_T4_SVC_NAP_NS 0      // service warp: nanosleep between polls of waits that are NOT on a tile's critical path
 #endif
 #ifndef RNF_T4_WORKER_REGS
 #define RNF_T4_WORKER_REGS 112
@@ -69,17 +78,19 @@ constexpr int kOffY = kOffAux + 2 * kAuxStride;           // [tile] Y block [128
 constexpr int kOffC = kOffY + kTiles * 4096;              // [tile] per-image block [64 x 16] fp16, no swizzle (2 KB)
 constexpr int kOffRed = kOffC + kTiles * 2048;            // [tile] reduction scratch
 constexpr int kOffBar = kOffRed + kTiles * 128;
-constexpr int kOffMisc = kOffBar + 8 * 16;
+constexpr int kOffMisc = kOffBar + 8 * 24;
 constexpr int kSmemBytes = kOffMisc + 64 + 64 * 8;
 constexpr int kSmemAlloc = kSmemBytes + 1024;
 static_assert(kOffLastW % 1024 == 0 && kW1Bytes % 1024 == 0, "UMMA SW128 tiles need 1024 B alignment");
 static_assert(kOffY % 16 == 0 && kOffC % 16 == 0 && kOffAux % 16 == 0, "no-swizzle blocks need 16 B alignment");
 
-// READY: hand-over of a tile's workers to its service warp (one arrival per worker warp).  Between two phases of this barrier the
-// workers always wait for a GEMM, i.e. for the service warp to have consumed the earlier phase: a parity wait cannot be lapped.
+// READY / READY2: hand-overs of a tile's workers to its service warp.  The second half of an epilogue has its own barrier: between
+// two phases of ONE barrier the workers always wait for a GEMM, i.e. for the service warp to have consumed the earlier phase, so a
+// parity wait can never be lapped (with a single barrier the two halves of an epilogue could both complete while the service warp
+// still waits for a weight piece, and a fast warp's second arrival would count towards the first phase).
 enum { BAR_W_FULL = 0 /* W1,W2,W3,W4 */, BAR_AUX_FULL = 4 /* [2] */, BAR_MMA = 6 /* [tile] */, BAR_READY = 6 + kTiles /* [tile] */,
-       BAR_COUNT = 6 + 2 * kTiles };
-static_assert(BAR_COUNT <= 16, "mbarrier slots");
+       BAR_READY2 = 6 + 2 * kTiles /* [tile] */, BAR_COUNT = 6 + 3 * kTiles };
+static_assert(BAR_COUNT <= 24, "mbarrier slots");
 
 // TMEM columns of a tile
 constexpr uint32_t kColAhi = 0, kColAlo = 32, kColD = 64, kColsPerTile = 128;
@@ -108,6 +119,16 @@ __device__ __forceinline__ void issue_split_ts(uint32_t d, uint32_t a_hi, uint32
   for (int k = 0; k < 4; ++k) umma_f16_ts(d, a_hi + 8 * k, b_lo + 2 * k, kDescHi, idesc, 1);
 #pragma unroll
   for (int k = 0; k < 4; ++k) umma_f16_ts(d, a_hi + 8 * k, b_hi + 2 * k, kDescHi, idesc, 1);
+}
+
+// ... the K steps k0, k0 + 1 of the three products: issued as soon as the HALF of the A operand they read has been handed over
+__device__ __forceinline__ void issue_split_ts_half(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t idesc, int k0) {
+#pragma unroll
+  for (int k = k0; k < k0 + 2; ++k) umma_f16_ts(d, a_lo + 8 * k, b_hi + 2 * k, kDescHi, idesc, 1);
+#pragma unroll
+  for (int k = k0; k < k0 + 2; ++k) umma_f16_ts(d, a_hi + 8 * k, b_lo + 2 * k, kDescHi, idesc, 1);
+#pragma unroll
+  for (int k = k0; k < k0 + 2; ++k) umma_f16_ts(d, a_hi + 8 * k, b_hi + 2 * k, kDescHi, idesc, 1);
 }
 
 __device__ __forceinline__ uint32_t pack_h2(__half lo, __half hi) {
@@ -170,10 +191,11 @@ __device__ __forceinline__ void relu_split_pair(float x0, float x1, uint32_t& hi
 }
 
 // Epilogue of one GEMM: my row of the accumulator -> (+ c) -> ReLU -> fp16 hi / lo -> A operand in TMEM (K element 2e in the
-// low half of column e).  All four 16-column loads are in flight before the first wait; the four stores are waited for once.
-// (Handing each half of the A operand over on its own, so that the next GEMM's first two K steps issue under the arithmetic of the
-// second half, costs 5 % more instructions and was measured 2 % slower in cycles: the switch is in the history, commit 1ac9139.)
-__device__ __forceinline__ void epilogue64(uint32_t tm, const float* cadd) {
+// low half of column e).  All four 16-column loads are in flight before the first wait.  The accumulator is in registers after
+// the loads, so each HALF of the A operand (K elements 0..31, then 32..63) is handed over on its own: the service warp issues the
+// next GEMM's first two K steps under the arithmetic of the second half.
+template <typename HandOver1, typename HandOver2>
+__device__ __forceinline__ void epilogue64(uint32_t tm, const float* cadd, HandOver1&& hand_over_first, HandOver2&& hand_over_second) {
   float a0[16], a1[16], a2[16], a3[16];
   tmem_ld16_async(tm + kColD, a0);
   tmem_ld16_async(tm + kColD + 16, a1);
@@ -199,8 +221,15 @@ __device__ __forceinline__ void epilogue64(uint32_t tm, const float* cadd) {
     }
     tmem_st16_nowait(tm + kColAhi + 16 * h, hi);
     tmem_st16_nowait(tm + kColAlo + 16 * h, lo);
+#if RNF_T4_HALF_EPI
+    tmem_st_wait();
+    if (h == 0) hand_over_first(); else hand_over_second();
+#endif
   }
+#if !RNF_T4_HALF_EPI
   tmem_st_wait();
+  hand_over_first();
+#endif
 }
 
 template <int N>
@@ -247,28 +276,41 @@ __device__ __forceinline__ void service_warp(const FlowArgs& a, uint8_t* smem, c
   const uint32_t w_hid_d = umma_desc_lo(smem_u32(smem + kOffW)), w_last_d = umma_desc_lo(smem_u32(smem + kOffLastW));
   const uint32_t bias_hid_d = umma_desc_lo_ns(smem_u32(smem + kOffW + 16384)), bias_last_d = umma_desc_lo_ns(smem_u32(smem + kOffLastW + 65536));
   const uint32_t aux_blk_d = umma_desc_lo_ns(smem_u32(smem + kOffAux + kAuxFirst));
-  const uint32_t bar_mma = bars + 8 * (BAR_MMA + tile), bar_ready = bars + 8 * (BAR_READY + tile);
-#if RNF_T4_DIRECT_WAIT_NS == 0
+  const uint32_t bar_mma = bars + 8 * (BAR_MMA + tile), bar_ready = bars + 8 * (BAR_READY + tile), bar_ready2 = bars + 8 * (BAR_READY2 + tile);
   const int bar_wait = 9 + tile;                     // named barrier the tile's workers sleep in during a GEMM round trip
-#endif
   constexpr uint32_t kIdesc = umma_idesc(128, 64);
   const uint32_t d = tm_tile + kColD;
   const int n_active = sc.n_active;
-  uint32_t par_mma = 0, par_ready = 0, par_w = 0;
+  uint32_t par_mma = 0, par_ready = 0, par_ready2 = 0, par_w = 0;
   int step = 0;
   int mob_cur = 0;
 
   auto wait_ready = [&]() {                          // the tile's four worker warps have handed over (Y block / A operand / drained D)
-    mbar_wait(bar_ready, par_ready);
+    mbar_wait_hint<RNF_T4_SVC_HINT_NS>(bar_ready, par_ready);
     par_ready ^= 1;
     tc_fence_after();
   };
-  auto mma_done = [&]() {                            // the GEMM just issued has completed (the pieces it read may be refilled)
-    mbar_wait(bar_mma, par_mma);
-    par_mma ^= 1;
+  auto wait_relaxed = [&](uint32_t bar, uint32_t parity) {   // a wait with slack (chunks 1..3, refill bookkeeping): naps between polls
+#if RNF_T4_SVC_NAP_NS > 0
+    while (!mbar_try_wait(bar, parity)) __nanosleep(RNF_T4_SVC_NAP_NS);
+#else
+    mbar_wait(bar, parity);
+#endif
+  };
+  auto wait_ready_second = [&]() {                   // ... second half of an epilogue
+    mbar_wait_hint<RNF_T4_SVC_HINT_NS>(bar_ready2, par_ready2);
+    par_ready2 ^= 1;
+    tc_fence_after();
+  };
+  auto wake_workers = [&]() {                        // the GEMM the workers sleep on has completed
 #if RNF_T4_DIRECT_WAIT_NS == 0
+    mbar_wait_hint<RNF_T4_SVC_HINT_NS>(bar_mma, par_mma);
+    par_mma ^= 1;
     tc_fence_before();
-    named_arrive(bar_wait, 128 + 32);                // wake the workers (by default they watch the mbarrier themselves)
+    named_arrive(bar_wait, 128 + 32);
+#else
+    wait_relaxed(bar_mma, par_mma);                  // the workers watch the mbarrier themselves; this wait only orders the refill bookkeeping
+    par_mma ^= 1;
 #endif
   };
 
@@ -286,20 +328,32 @@ __device__ __forceinline__ void service_warp(const FlowArgs& a, uint8_t* smem, c
       for (int l = 0; l < 4; ++l) {
         if (l == 0) mbar_wait(bars + 8 * (BAR_AUX_FULL + abuf), (uint32_t)((step >> 1) & 1));
         else mbar_wait(bars + 8 * (BAR_W_FULL + l - 1), (par_w >> (l - 1)) & 1u);
-        wait_ready();                                // l == 0: Y block written; l > 0: A operand of the previous epilogue stored
-        if (elect_one_sync()) {
-          if (l == 0) {
+        wait_ready();                                // l == 0: Y block written; l > 0: first half of the A operand (K 0..31)
+        if (l == 0) {
+          if (elect_one_sync()) {
             umma_f16(d, y_d, aux_blk_d + abuf * (kAuxStride >> 4), kDescHiNS, kIdesc, 0);
-          } else {
-            const uint32_t wb = w_hid_d + (l - 1) * (kW1Bytes >> 4);
-            umma_f16(d, y_d, bias_hid_d + (l - 1) * (kW1Bytes >> 4), kDescHiNS, kIdesc, 0);
-            issue_split_ts(d, tm_tile + kColAhi, tm_tile + kColAlo, wb, wb + (8192 >> 4), kIdesc);
+            if (c_by_mma) umma_f16(d, y_d, c_d, kDescHiNS, kIdesc, 1);
+            umma_commit(bar_mma);
           }
-          if (c_by_mma && (l == 0 || l == 3)) umma_f16(d, y_d, c_d, kDescHiNS, kIdesc, 1);
-          umma_commit(bar_mma);
+          __syncwarp();
+        } else {
+          const uint32_t wb = w_hid_d + (l - 1) * (kW1Bytes >> 4);
+          if (elect_one_sync()) {
+            umma_f16(d, y_d, bias_hid_d + (l - 1) * (kW1Bytes >> 4), kDescHiNS, kIdesc, 0);
+            issue_split_ts_half(d, tm_tile + kColAhi, tm_tile + kColAlo, wb, wb + (8192 >> 4), kIdesc, 0);
+          }
+          __syncwarp();
+#if RNF_T4_HALF_EPI
+          wait_ready_second();                       // second half (K 32..63)
+#endif
+          if (elect_one_sync()) {
+            issue_split_ts_half(d, tm_tile + kColAhi, tm_tile + kColAlo, wb, wb + (8192 >> 4), kIdesc, 2);
+            if (c_by_mma && l == 3) umma_f16(d, y_d, c_d, kDescHiNS, kIdesc, 1);
+            umma_commit(bar_mma);
+          }
+          __syncwarp();
         }
-        __syncwarp();
-        mma_done();
+        wake_workers();
         // a piece is dead once ALL tiles' GEMM that reads it has completed: the last tile to get here refills it
         if (lane == 0) {
           if (l == 0) { if ((atomicAdd(&s_cnt[4 + abuf], 1) % n_active) == n_active - 1 && step + 2 < sc.total_steps) load_piece(mob_n2, 4, abuf); }
@@ -312,24 +366,46 @@ __device__ __forceinline__ void service_warp(const FlowArgs& a, uint8_t* smem, c
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         const uint32_t wb = w_last_d + c * (8192 >> 4);                    // rows 64c .. 64c+63 of the hi plane
-        wait_ready();                                // c == 0: last hidden epilogue done; c > 0: chunk c - 1 drained into registers
-        if (elect_one_sync()) {
-          umma_f16(d, y_d, bias_last_d + c * (2048 >> 4), kDescHiNS, kIdesc, 0);
-          issue_split_ts(d, tm_tile + kColAhi, tm_tile + kColAlo, wb, wb + (32768 >> 4), kIdesc);
-          umma_commit(bar_mma);
-        }
-        __syncwarp();
         if (c == 0) {
-          mma_done();
+          wait_ready();                              // (first half of) the last hidden epilogue
+        } else {                                     // chunk c - 1 drained into registers; the workers have ~1.5 k cycles of arithmetic left
+          wait_relaxed(bar_ready, par_ready);
+          par_ready ^= 1;
+          tc_fence_after();
+        }
+        if (c == 0) {
+          if (elect_one_sync()) {
+            umma_f16(d, y_d, bias_last_d, kDescHiNS, kIdesc, 0);
+            issue_split_ts_half(d, tm_tile + kColAhi, tm_tile + kColAlo, wb, wb + (32768 >> 4), kIdesc, 0);
+          }
+          __syncwarp();
+#if RNF_T4_HALF_EPI
+          wait_ready_second();                       // second half
+#endif
+          if (elect_one_sync()) {
+            issue_split_ts_half(d, tm_tile + kColAhi, tm_tile + kColAlo, wb, wb + (32768 >> 4), kIdesc, 2);
+            umma_commit(bar_mma);
+          }
+          __syncwarp();
+        } else {
+          if (elect_one_sync()) {
+            umma_f16(d, y_d, bias_last_d + c * (2048 >> 4), kDescHiNS, kIdesc, 0);
+            issue_split_ts(d, tm_tile + kColAhi, tm_tile + kColAlo, wb, wb + (32768 >> 4), kIdesc);
+            umma_commit(bar_mma);
+          }
+          __syncwarp();
+        }
+        if (c == 0) {
+          wake_workers();
         } else if (c == 3) {
           // W4 is dead the moment the last chunk's MMAs have completed (not after the arithmetic on it): the last tile to see
           // that refills it.
-          mbar_wait(bar_mma, par_mma);
+          wait_relaxed(bar_mma, par_mma);
           par_mma ^= 1;
           if (lane == 0 && (atomicAdd(&s_cnt[3], 1) % n_active) == n_active - 1 && step + 1 < sc.total_steps) load_piece(mob_n1, 3, 0);
           __syncwarp();
         } else {
-          par_mma ^= 1;                              // chunks 1, 2: only the workers wait for them
+          par_mma ^= 1;                              // chunks 1, 2: the workers poll the mbarrier themselves
         }
       }
       par_w ^= 0xFu;
@@ -395,10 +471,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
     const uint32_t tm = tmem_base + (uint32_t)tile * kColsPerTile + ((uint32_t)((warp & 3) * 32) << 16);   // my warp's lane quarter
     uint8_t* y_blk = smem + kOffY + tile * 4096;
     uint8_t* c_blk = smem + kOffC + tile * 2048;
-#if RNF_T4_DIRECT_WAIT_NS == 0
     const int bar_wait = 9 + tile;                     // named barrier: the tile's workers sleep here during a GEMM round trip
-#endif
-    const uint32_t bar_mma = bars + 8 * (BAR_MMA + tile), bar_ready = bars + 8 * (BAR_READY + tile);
+    const uint32_t bar_mma = bars + 8 * (BAR_MMA + tile), bar_ready = bars + 8 * (BAR_READY + tile), bar_ready2 = bars + 8 * (BAR_READY2 + tile);
     uint32_t par_mma = 0;
 #if RNF_TC_TRACE
     int64_t step = 0;
@@ -410,6 +484,11 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ready);
+    };
+    auto hand_over_second = [&]() {                    // second half of an epilogue (its own mbarrier, see BAR_READY2)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ready2);
     };
     // Wait for a GEMM that the tile cannot overlap with anything (the dependent round trips of the chain).  Default: every worker
     // warp watches the MMA's mbarrier itself (try_wait with a suspend hint).  Alternative (RNF_T4_DIRECT_WAIT_NS = 0): the workers
@@ -528,8 +607,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
           wait_mma_long();
           TRACE(3 + 3 * l);
           const float* ca = (l == 0 || l == 3) ? cadd : nullptr;
-          epilogue64(tm, ca);
-          hand_over();
+          epilogue64(tm, ca, hand_over, hand_over_second);
           TRACE(4 + 3 * l);
         }
         // ---- fc_last in four N = 64 chunks through the single accumulator; 16 mixture components per chunk ----
