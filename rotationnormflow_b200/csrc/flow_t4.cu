@@ -724,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_t4_kernel(const FlowArgs a) 
 // with a tiles in flight).  Round durations measured with the RNF_T4_ACTIVE override on raw.yml, eight full rounds each
 // (tools/active_tiles_probe.py, profiles/r02_active_tiles_service.txt): 112 / 171 / 238 / 264 M rot/s with 1 / 2 / 3 / 4 tiles in
 // flight, i.e. a round of one tile lasts 0.59 of a round of four, two 0.77, three 0.83.
-static int pick_active_tiles(int64_t n_tiles, int sm_count) {
+int pick_active_tiles(int64_t n_tiles, int sm_count) {
   static const float kRound[5] = {0.f, 0.589f, 0.772f, 0.834f, 1.0f};
   int best = kTiles;
   float best_cost = 1e30f;

@@ -34,6 +34,7 @@ namespace rnf {
 cudaError_t launch_flow_row(const FlowArgs& a, bool inverse, int sm_count, cudaStream_t st);
 cudaError_t launch_flow_t4(const FlowArgs& a, int sm_count, cudaStream_t st);
 bool flow_tc_supported(const rnf_flow* f);
+int pick_active_tiles(int64_t n_tiles, int sm_count);
 }  // namespace rnf
 
 extern "C" {
@@ -43,6 +44,9 @@ void rnf_debug_set_trace(long long* dev_ptr) { g_trace = dev_ptr; }
 // measurement hook (not part of the ABI header; bench.py): device counter that the inverse kernel increments by 32 per warp,
 // Mobius layer and evaluation of the mixture map F, i.e. by the number of (sample, layer, evaluation) triples executed
 void rnf_debug_set_probe_counter(unsigned long long* dev_ptr) { g_probe_counter = dev_ptr; }
+
+// test hook (not part of the ABI header; host logic only, no device needed): tile slots flow_t4 would use for a launch of n_tiles
+int rnf_debug_pick_active_tiles(long long n_tiles, int sm_count) { return rnf::pick_active_tiles((int64_t)n_tiles, sm_count); }
 
 int rnf_abi_version(void) { return RNF_ABI_VERSION; }
 

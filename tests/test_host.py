@@ -290,3 +290,26 @@ def test_merge_partials_equals_global_reduction():
                                         torch.stack(am + [torch.zeros(B, dtype=torch.int64)]),
                                         torch.stack(se + [torch.zeros(B)]))
     assert torch.equal(idx2, idx) and torch.allclose(s2, s)
+
+
+def test_tile_slots_per_launch_host_logic():
+    """flow_t4 chooses how many of its four tile slots a launch uses (csrc/flow_t4.cu: pick_active_tiles, a host function): it minimises
+    rounds x measured round duration.  Large launches use all four; launches of a few tiles per SM take the count that wastes the least
+    of the last round; the choice never exceeds the work there is."""
+    import ctypes as C
+    from rotationnormflow_b200 import _cabi
+    lib = C.CDLL(_cabi.library_path())
+    f = lib.rnf_debug_pick_active_tiles
+    f.argtypes, f.restype = [C.c_longlong, C.c_int], C.c_int
+    sms = 148
+    rel = {1: 0.589, 2: 0.772, 3: 0.834, 4: 1.0}                      # round durations, profiles/r02_active_tiles_service.txt
+    def cost(n, a):
+        groups = -(-n // a)
+        return -(-groups // sms) * rel[a]
+    for n in [1, 5, 147, 148, 149, 296, 391, 443, 444, 445, 592, 593, 782, 1563, 18432, 147456, 2_359_296]:
+        a = f(n, sms)
+        assert 1 <= a <= 4
+        assert cost(n, a) <= min(cost(n, b) for b in (1, 2, 3, 4)) + 1e-6, (n, a)
+    assert f(147456, sms) == 4 and f(18432, sms) == 4                    # bench workloads: all four slots
+    assert f(782, sms) == 3                                              # config 1 (100 000 rows): two rounds of three
+    assert f(100, sms) == 1                                              # fewer tiles than SMs: one slot per CTA is the shortest round
